@@ -1,0 +1,163 @@
+/*
+ * b200_paged_attn.h -- C ABI of libb200attn.so, the B200 (sm_100a) paged-attention path that
+ * drops in behind nano-vLLM's attention operator and the small fused ops around it.
+ *
+ * Every entry point cites the reference interface (GeeeekExplorer/nano-vllm @ bb823b3e) it
+ * replaces.  The reference has no FFI layer of its own: its seams are Python-level
+ * (SURVEY.md section 8b), so this header is the binding a maintainer would load with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - returns 0 on success, a negative B200_E* code otherwise (b200_strerror names it);
+ *   - the caller owns every buffer (device pointers from the PyTorch allocator);
+ *     the library allocates nothing after b200_init / b200_kv_bind;
+ *   - nothing synchronises the host; every launch goes to the stream passed in, so a whole
+ *     decode step is CUDA-graph capturable; per-step variation flows only through
+ *     device-resident metadata (block_tables, context_lens, slot_mapping, cu_seqlens);
+ *   - no C++ or torch types cross the boundary; `stream` is a cudaStream_t passed as void*;
+ *   - one b200_ctx per process/GPU, not thread-safe (one engine thread per rank, like the
+ *     reference's ModelRunner, engine/model_runner.py:17-48).
+ *
+ * Dtypes match the tensors the reference builds (engine/model_runner.py:129-188):
+ *   activations / caches  bf16;   input_ids, positions  int64;
+ *   slot_mapping, context_lens, block_tables, cu_seqlens  int32.
+ *
+ * KV-cache layout in HBM (ours; only block ids and slot numbers are contract):
+ *   k_base, v_base : [layers][num_blocks][num_kv_heads][block_size][head_dim] bf16
+ *   slot s  ->  block = s / block_size, row = s % block_size   (model_runner.py:151-161,181)
+ *   so one (block, kv head) page is block_size*head_dim*2 contiguous bytes.
+ */
+#ifndef B200_PAGED_ATTN_H
+#define B200_PAGED_ATTN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+enum {
+    B200_OK = 0,
+    B200_EINVAL = -1,       /* bad argument (null pointer, unsupported shape) */
+    B200_EUNSUPPORTED = -2, /* head_dim != 128, group size not in {1,2,4,8}, block_size not a power of two in [16,256] */
+    B200_ECUDA = -3,        /* a CUDA runtime call failed; b200_last_cuda_error() has the text */
+    B200_ENOTBOUND = -4,    /* KV cache not bound (b200_kv_bind) */
+    B200_EWORKSPACE = -5,   /* workspace too small */
+    B200_EARCH = -6         /* device is not compute capability 10.x */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+
+/* Replaces the device setup in ModelRunner.__init__ (engine/model_runner.py:26-30): selects
+ * `device`, checks it is sm_100, records the SM count.  */
+int b200_init(int device, b200_ctx** out);
+void b200_destroy(b200_ctx* ctx);
+const char* b200_strerror(int code);
+const char* b200_last_cuda_error(b200_ctx* ctx);
+int b200_sm_count(const b200_ctx* ctx);
+/* ABI version of this header; bumped on any signature change. */
+int b200_abi_version(void);
+
+/* Replaces the per-module k_cache / v_cache binding of ModelRunner.allocate_kv_cache
+ * (engine/model_runner.py:103-121).  The caller allocates 2 * layers * num_blocks * num_kv_heads *
+ * block_size * head_dim bf16 elements (layout above) and hands over the two base pointers. */
+int b200_kv_bind(b200_ctx* ctx, void* k_base, void* v_base, int layers, int64_t num_blocks,
+                 int block_size, int num_kv_heads, int head_dim);
+
+/* Bytes of scratch b200_paged_decode needs for batches up to max_batch with num_q_heads query
+ * heads.  The caller zero-fills it once; the kernel leaves its counters zeroed. */
+size_t b200_decode_workspace_bytes(const b200_ctx* ctx, int max_batch, int num_q_heads);
+
+/* ---- the attention operator (layers/attention.py) -------------------------------------- */
+
+/* store_kvcache (layers/attention.py:10-40): for i < n with slot_mapping[i] != -1 copy
+ * k[i] (num_kv_heads*head_dim bf16, row stride k_stride0 elements) and v[i] into slot
+ * slot_mapping[i] of layer `layer`. */
+int b200_store_kv(b200_ctx* ctx, int layer, const void* k, int64_t k_stride0, const void* v,
+                  int64_t v_stride0, const int32_t* slot_mapping, int n, void* stream);
+
+/* Decode branch of Attention.forward (layers/attention.py:71-74), i.e.
+ * flash_attn_with_kvcache(q.unsqueeze(1), k_cache, v_cache, cache_seqlens=context_lens,
+ * block_table=block_tables, softmax_scale=scale, causal=True):
+ *   out[b,h,:] = softmax(scale * q[b,h,:] K_b^T) V_b over keys 0..context_lens[b]-1 reached
+ *   through block_tables[b, j / block_size].  Rows with context_lens[b] == 0 (graph padding,
+ *   model_runner.py:207) write zeros.
+ * q, out: [batch, num_q_heads, head_dim] bf16 with row strides in elements. */
+int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0,
+                      const int32_t* block_tables, int bt_stride, const int32_t* context_lens,
+                      void* out, int64_t out_stride0, int batch, int num_q_heads, float scale,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Prefill branch of Attention.forward (layers/attention.py:64-70), i.e.
+ * flash_attn_varlen_func(q, k, v, cu_seqlens_q/k, max_seqlen_q/k, softmax_scale=scale,
+ * causal=True, block_table=block_tables): bottom-right aligned causal mask, query i of a
+ * sequence sees keys j <= i + len_k - len_q.
+ *   block_tables == NULL : k, v are the packed [total_k, num_kv_heads, head_dim] rows
+ *                          (row strides in elements), cu_seqlens_k indexes them.
+ *   block_tables != NULL : prefix-cache hit / chunked prefill (attention.py:65-66): keys and
+ *                          values are read from the bound cache of `layer`; k, v ignored. */
+int b200_paged_prefill(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0, const void* k,
+                       int64_t k_stride0, const void* v, int64_t v_stride0,
+                       const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                       const int32_t* block_tables, int bt_stride, void* out, int64_t out_stride0,
+                       int total_q, int num_seqs, int max_seqlen_q, int max_seqlen_k,
+                       int num_q_heads, int num_kv_heads, float scale, void* stream);
+
+/* ---- the fused ops around it (the reference's five @torch.compile sites) ---------------- */
+
+/* RMSNorm.rms_forward (layers/layernorm.py:16-26): out = x * rsqrt(mean(x^2)+eps) * w, fp32
+ * math, one rounding.  x/out: [rows, cols] bf16 with row strides. */
+int b200_rmsnorm(const void* x, int64_t x_stride0, const void* weight, void* out,
+                 int64_t out_stride0, int rows, int cols, float eps, void* stream);
+
+/* RMSNorm.add_rms_forward (layers/layernorm.py:28-40): residual <- bf16(x + residual);
+ * out = norm(x + residual) * w with the variance taken on the un-rounded fp32 sum. */
+int b200_add_rmsnorm(const void* x, void* residual, const void* weight, void* out, int rows,
+                     int cols, float eps, void* stream);
+
+/* q_norm + k_norm + rotary_emb + store_kvcache of Qwen3Attention.forward (models/qwen3.py:82-86,
+ * layers/rotary_embedding.py:37-48, layers/attention.py:62-63) in one pass over the fused qkv
+ * GEMM output: per token, per head RMSNorm over head_dim (rounded to bf16 as the reference's
+ * separate kernel does), NeoX rotation with cos_sin[positions[i]] (fp32 [max_pos, head_dim] =
+ * cat(cos, sin)), q and k rewritten in place, k and v scattered to slot_mapping[i] of `layer`
+ * when slot_mapping != NULL and a cache is bound.
+ * qkv: [n, (num_q_heads + 2*num_kv_heads) * head_dim] bf16, row stride qkv_stride0. */
+int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64_t qkv_stride0,
+                           int num_q_heads, int num_kv_heads, const int64_t* positions,
+                           const void* q_norm_weight, const void* k_norm_weight,
+                           const float* cos_sin, float eps, const int32_t* slot_mapping, int n,
+                           void* stream);
+
+/* SiluAndMul.forward (layers/activation.py:8-11): out[r, c] = silu(x[r, c]) * x[r, inter + c]. */
+int b200_silu_mul(const void* x, void* out, int rows, int inter, void* stream);
+
+/* F.embedding of VocabParallelEmbedding.forward (layers/embed_head.py:34-42), single shard. */
+int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden,
+                   void* stream);
+
+/* Sampler.forward (layers/sampler.py:7-12) plus the greedy branch the north-star adds:
+ *   temperature[r] == 0 : out[r] = argmax_j logits[r, j]  (lowest index on ties)
+ *   temperature[r]  > 0 : exponential race  argmax_j softmax(logits/t)_j / E_j,  E_j ~ Exp(1)
+ *                         computed as argmax_j (logits[r,j]/t - log E_j), counter-based RNG
+ *                         keyed by (seed, step, r, index_offset + j); when step_dev != NULL the
+ *                         device value *step_dev is added to step at run time, so a captured
+ *                         CUDA graph draws fresh noise on every replay.
+ * logits: [rows, vocab] bf16 (logits_is_fp32 == 0) or fp32, row stride in elements.
+ * out: [rows] int64 token ids = index_offset + winning column (the dtype Sampler returns).
+ * Vocab-parallel use (replaces the dist.gather of ParallelLMHead.forward, layers/embed_head.py:62-65):
+ * each rank passes its shard with index_offset = first vocab id of the shard and a non-NULL
+ * out_keys; out_keys[r] is an int64 whose signed order is (winning score, then lower token id),
+ * so one all-reduce(MAX) over ranks picks the global winner:
+ *   token = 0xffffffff - (key & 0xffffffff).   out may be NULL when out_keys is given. */
+int b200_sample(const void* logits, int logits_is_fp32, int64_t logits_stride0,
+                const float* temperatures, int rows, int vocab, int64_t index_offset,
+                uint64_t seed, uint64_t step, const int64_t* step_dev, int64_t* out,
+                int64_t* out_keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_PAGED_ATTN_H */

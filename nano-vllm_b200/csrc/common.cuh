@@ -1,0 +1,147 @@
+// Shared device helpers and the context struct behind include/b200_paged_attn.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "b200_paged_attn.h"
+
+#define B200_HEAD_DIM 128
+
+struct b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // bound KV cache (layout [layers][num_blocks][num_kv_heads][block_size][head_dim])
+    __nv_bfloat16* k_base = nullptr;
+    __nv_bfloat16* v_base = nullptr;
+    int layers = 0;
+    int64_t num_blocks = 0;
+    int block_size = 0;
+    int block_shift = 0;
+    int num_kv_heads = 0;
+    int head_dim = 0;
+    std::string last_cuda_error;
+
+    size_t layer_elems() const {
+        return (size_t)num_blocks * num_kv_heads * block_size * head_dim;
+    }
+    __nv_bfloat16* k_layer(int l) const { return k_base + (size_t)l * layer_elems(); }
+    __nv_bfloat16* v_layer(int l) const { return v_base + (size_t)l * layer_elems(); }
+};
+
+#define B200_CUDA_CHECK(ctx, expr)                                   \
+    do {                                                              \
+        cudaError_t _e = (expr);                                      \
+        if (_e != cudaSuccess) {                                      \
+            if (ctx) (ctx)->last_cuda_error = cudaGetErrorString(_e); \
+            return B200_ECUDA;                                        \
+        }                                                             \
+    } while (0)
+
+static inline int b200_launch_status(b200_ctx* ctx) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        if (ctx) ctx->last_cuda_error = cudaGetErrorString(e);
+        return B200_ECUDA;
+    }
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 <-> fp32 on packed words.  A bf16 is the high half of an fp32, so unpacking is one
+// shift / one mask (ALU pipe), leaving the FMA pipe to the dot products.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits)
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__device__ __forceinline__ float round_bf16(float x) {
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
+    f[0] = bf16lo(w.x); f[1] = bf16hi(w.x);
+    f[2] = bf16lo(w.y); f[3] = bf16hi(w.y);
+    f[4] = bf16lo(w.z); f[5] = bf16hi(w.z);
+    f[6] = bf16lo(w.w); f[7] = bf16hi(w.w);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 w;
+    w.x = pack_bf16x2(f[0], f[1]);
+    w.y = pack_bf16x2(f[2], f[3]);
+    w.z = pack_bf16x2(f[4], f[5]);
+    w.w = pack_bf16x2(f[6], f[7]);
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// warp reductions
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA engine, SASS: UBLKCP / SYNCS)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the inits visible to the async proxy before any bulk copy signals them
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+// size must be a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+static inline int ilog2_exact(int v) {
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return ((1 << s) == v) ? s : -1;
+}

@@ -1,0 +1,498 @@
+// Single-token paged decode attention for sm_100a.
+//
+// Replaces the decode branch of the reference's Attention.forward (nanovllm/layers/attention.py:71-74,
+// flash_attn_with_kvcache over paged K/V).  HBM-bandwidth bound: every K/V byte of every live
+// context token is read exactly once per layer per step.
+//
+// Design (DESIGN.md "decode kernel"):
+//   * one persistent launch, one CTA per SM, NWARPS independent warps per CTA;
+//   * the step's work is the list of 16-token chunks ordered by (sequence, kv head, chunk);
+//     it is cut into equal contiguous ranges, one per warp ("stream-K" over KV pages), so the
+//     load is balanced to one chunk whatever the mix of context lengths;
+//   * each warp streams its chunks through a private NSTAGES-deep ring in shared memory with
+//     1-D bulk async copies (TMA engine, cp.async.bulk -> SASS UBLKCP) completing on mbarriers;
+//     a (page, kv head) tile is contiguous in HBM so every copy is one linear 4 KB burst;
+//   * QK^T and PV run on the fp32 FMA pipe with all G q-heads of the kv head sharing each K/V
+//     read; softmax statistics via warp shuffles;
+//   * a kv-head's context that straddles several warps leaves (m, l, O) partials in a small
+//     workspace; the last warp to arrive (per-pair counter) merges them in fixed order, so the
+//     result is deterministic and no second launch is needed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CHUNK = 16;                          // tokens per pipeline stage
+constexpr int ROW_BYTES = B200_HEAD_DIM * 2;       // one token of one kv head
+constexpr int CHUNK_BYTES = CHUNK * ROW_BYTES;     // 4096
+constexpr int MAX_BATCH = 1024;                    // sequences per launch (prefix table in smem)
+
+struct DecodeParams {
+    const __nv_bfloat16* q;
+    int64_t q_stride;
+    __nv_bfloat16* out;
+    int64_t out_stride;
+    const __nv_bfloat16* k_layer;
+    const __nv_bfloat16* v_layer;
+    const int32_t* block_tables;
+    int bt_stride;
+    const int32_t* context_lens;
+    int batch;
+    int hkv;
+    int block_shift;
+    float scale_log2;
+    float* part_o;    // [slots][G][128]
+    float* part_ml;   // [slots][G][2]
+    int* counters;    // [batch * hkv], zero on entry, zero on exit
+};
+
+template <int G, int NWARPS, int NSTAGES>
+struct DecodeSmem {
+    static constexpr int kStageBytes = 2 * CHUNK_BYTES;
+    static constexpr int kWarpBytes = NSTAGES * kStageBytes;
+    static constexpr int kOffStages = 0;
+    static constexpr int kOffCum = NWARPS * kWarpBytes;                 // int[MAX_BATCH + 1]
+    static constexpr int kOffCtx = kOffCum + (MAX_BATCH + 4) * 4;       // int[MAX_BATCH]
+    static constexpr int kOffBars = kOffCtx + MAX_BATCH * 4;            // u64[NWARPS][NSTAGES]
+    static constexpr int kOffP = kOffBars + NWARPS * NSTAGES * 8;       // float[NWARPS][G][16]
+    static constexpr int kOffWarpTot = kOffP + NWARPS * G * 16 * 4;     // int[NWARPS]
+    static constexpr int kTotal = kOffWarpTot + 32 * 4;
+};
+
+// Walks chunks in (sequence, kv head, chunk) order.  Warp-uniform.
+struct ChunkCursor {
+    int b, h, ck, n, ctx;
+    __device__ __forceinline__ void seek(const int* cum, const int* ctxs, int batch, int hkv, long long c) {
+        int key = (int)(c / hkv);
+        int lo = 0, hi = batch;            // largest b with cum[b] <= key
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (cum[mid] <= key) lo = mid; else hi = mid;
+        }
+        b = lo;
+        n = cum[b + 1] - cum[b];
+        ctx = ctxs[b];
+        int rem = (int)(c - (long long)hkv * cum[b]);
+        h = rem / n;
+        ck = rem - h * n;
+    }
+    __device__ __forceinline__ void advance(const int* cum, const int* ctxs, int batch, int hkv) {
+        if (++ck < n) return;
+        ck = 0;
+        if (++h < hkv) return;
+        h = 0;
+        do { ++b; } while (b < batch && cum[b + 1] == cum[b]);
+        if (b < batch) { n = cum[b + 1] - cum[b]; ctx = ctxs[b]; }
+    }
+};
+
+template <int G, int NWARPS, int NSTAGES>
+__global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const DecodeParams p) {
+    using L = DecodeSmem<G, NWARPS, NSTAGES>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    int* cum = reinterpret_cast<int*>(smem + L::kOffCum);
+    int* ctxs = reinterpret_cast<int*>(smem + L::kOffCtx);
+    int* warp_tot = reinterpret_cast<int*>(smem + L::kOffWarpTot);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int batch = p.batch;
+    const int hkv = p.hkv;
+
+    uint8_t* my_stages = smem + L::kOffStages + warp * L::kWarpBytes;
+    const uint32_t my_stages_u32 = smem_u32(my_stages);
+    const uint32_t my_bars_u32 = smem_u32(smem + L::kOffBars) + warp * NSTAGES * 8;
+    float* pbuf = reinterpret_cast<float*>(smem + L::kOffP) + warp * G * 16;
+
+    // ---- per-warp ring setup: zero the stages (stale rows of a partial chunk must stay finite),
+    //      init the mbarriers -------------------------------------------------------------------
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* s4 = reinterpret_cast<uint4*>(my_stages);
+        for (int i = lane; i < L::kWarpBytes / 16; i += 32) s4[i] = z;
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGES; ++s) mbar_init(my_bars_u32 + s * 8, 1);
+            mbar_fence_init();
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+
+    // ---- exclusive prefix of per-sequence chunk counts ------------------------------------------
+    constexpr int NT = NWARPS * 32;
+    constexpr int IPT = (MAX_BATCH + NT - 1) / NT;
+    {
+        int vals[IPT];
+        int tsum = 0;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            int idx = tid * IPT + i;
+            int c = 0;
+            if (idx < batch) {
+                c = p.context_lens[idx];
+                c = c < 0 ? 0 : c;
+                ctxs[idx] = c;
+            }
+            vals[i] = (c + CHUNK - 1) / CHUNK;
+            tsum += vals[i];
+        }
+        int inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int nb = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nb;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            int t = warp_tot[w];
+            if (w < warp) woff += t;
+            total += t;
+        }
+        int excl = woff + inc - tsum;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            int idx = tid * IPT + i;
+            if (idx < batch) cum[idx] = excl;
+            excl += vals[i];
+        }
+        if (tid == 0) cum[batch] = total;
+        __syncthreads();
+    }
+
+    // ---- rows without context (CUDA-graph padding) produce zeros --------------------------------
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        if (ctxs[b] == 0) {
+            const int n16 = hkv * G * (B200_HEAD_DIM / 8);
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + (int64_t)b * p.out_stride);
+            for (int i = tid; i < n16; i += NT) o4[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+
+    // ---- this warp's contiguous chunk range -----------------------------------------------------
+    const long long C = (long long)hkv * cum[batch];
+    const int TW = gridDim.x * NWARPS;
+    const int gw = blockIdx.x * NWARPS + warp;
+    if (C == 0) return;
+    const long long TWe = C < TW ? C : (long long)TW;     // workers that get at least one chunk
+    if (gw >= TWe) return;
+    const long long c_begin = (long long)gw * C / TWe;
+    const long long c_end = (long long)(gw + 1) * C / TWe;
+    const int n_local = (int)(c_end - c_begin);
+
+    ChunkCursor pi, ci;                                   // producer (issue) / consumer cursors
+    pi.seek(cum, ctxs, batch, hkv, c_begin);
+    ci = pi;
+
+    const int hw = lane >> 4;                             // which token of a pair this half-warp owns
+    const int j = lane & 15;                              // which 8-wide slice of head_dim
+    const int bs_mask = (1 << p.block_shift) - 1;
+
+    auto issue = [&](int i) {                             // chunk i of this warp's range
+        if (lane == 0) {
+            const int slot = i % NSTAGES;
+            const int tok0 = pi.ck * CHUNK;
+            const int page = p.block_tables[(int64_t)pi.b * p.bt_stride + (tok0 >> p.block_shift)];
+            int valid = pi.ctx - tok0;
+            valid = valid > CHUNK ? CHUNK : valid;
+            const uint32_t bytes = (uint32_t)valid * ROW_BYTES;
+            const int64_t row = (((int64_t)page * hkv + pi.h) << p.block_shift) + (tok0 & bs_mask);
+            const uint32_t bar = my_bars_u32 + slot * 8;
+            const uint32_t dst = my_stages_u32 + slot * L::kStageBytes;
+            mbar_expect_tx(bar, 2 * bytes);
+            bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
+            bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
+        }
+        pi.advance(cum, ctxs, batch, hkv);
+    };
+
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < NSTAGES - 1 && i < n_local; ++i) issue(i);
+
+    float qf[G][8];
+    float o[G][8];
+    float m[G], l[G];
+    bool seg_start = true;
+
+#pragma unroll 1
+    for (int i = 0; i < n_local; ++i) {
+        if (i + NSTAGES - 1 < n_local) issue(i + NSTAGES - 1);
+
+        if (seg_start) {
+            seg_start = false;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint4 w = *reinterpret_cast<const uint4*>(
+                    p.q + (int64_t)ci.b * p.q_stride + (ci.h * G + g) * B200_HEAD_DIM + j * 8);
+                unpack8(w, qf[g]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { qf[g][e] *= p.scale_log2; o[g][e] = 0.f; }
+                m[g] = -INFINITY;
+                l[g] = 0.f;
+            }
+        }
+
+        const int slot = i % NSTAGES;
+        mbar_wait(my_bars_u32 + slot * 8, (i / NSTAGES) & 1);
+        const uint8_t* ks = my_stages + slot * L::kStageBytes;
+        const uint8_t* vs = ks + CHUNK_BYTES;
+
+        // ---- S = q K^T : half-warp per token, 16 lanes x 8 dims ---------------------------------
+        float acc[G][8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint4 w = *reinterpret_cast<const uint4*>(ks + (2 * it + hw) * ROW_BYTES + j * 16);
+            float kf[8];
+            unpack8(w, kf);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float a = qf[g][0] * kf[0];
+#pragma unroll
+                for (int e = 1; e < 8; ++e) a = fmaf(qf[g][e], kf[e], a);
+                acc[g][it] = a;
+            }
+        }
+        // reduce over the 16 dim-slices, scattering tokens over lanes: 8 -> 4 -> 2 -> 1 values
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const float send = (j & 8) ? acc[g][x] : acc[g][x + 4];
+                const float keep = (j & 8) ? acc[g][x + 4] : acc[g][x];
+                acc[g][x] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                const float send = (j & 4) ? acc[g][x] : acc[g][x + 2];
+                const float keep = (j & 4) ? acc[g][x + 2] : acc[g][x];
+                acc[g][x] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            {
+                const float send = (j & 2) ? acc[g][0] : acc[g][1];
+                const float keep = (j & 2) ? acc[g][1] : acc[g][0];
+                acc[g][0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            acc[g][0] += __shfl_xor_sync(0xffffffffu, acc[g][0], 1);
+        }
+        // this lane now holds the score of token  t = 2*it + hw,  it = bits (3,2,1) of j
+        const int my_it = ((j >> 3) & 1) * 4 + ((j >> 2) & 1) * 2 + ((j >> 1) & 1);
+        const int my_t = 2 * my_it + hw;
+        int nvalid = ci.ctx - ci.ck * CHUNK;
+        nvalid = nvalid > CHUNK ? CHUNK : nvalid;
+        const bool tok_ok = my_t < nvalid;
+
+        // ---- online softmax ---------------------------------------------------------------------
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float s = tok_ok ? acc[g][0] : -INFINITY;
+            const float m_new = fmaxf(m[g], warp_max(s));
+            const float alpha = fast_exp2(m[g] - m_new);
+            const float pv = fast_exp2(s - m_new);
+            m[g] = m_new;
+            l[g] = l[g] * alpha + ((j & 1) ? 0.f : pv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[g][e] *= alpha;
+            if (!(j & 1)) pbuf[g * 16 + hw * 8 + my_it] = pv;
+        }
+        __syncwarp();
+
+        // ---- O += P V ---------------------------------------------------------------------------
+        float pr[G][8];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float4 a = *reinterpret_cast<const float4*>(pbuf + g * 16 + hw * 8);
+            const float4 c4 = *reinterpret_cast<const float4*>(pbuf + g * 16 + hw * 8 + 4);
+            pr[g][0] = a.x; pr[g][1] = a.y; pr[g][2] = a.z; pr[g][3] = a.w;
+            pr[g][4] = c4.x; pr[g][5] = c4.y; pr[g][6] = c4.z; pr[g][7] = c4.w;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint4 w = *reinterpret_cast<const uint4*>(vs + (2 * it + hw) * ROW_BYTES + j * 16);
+            float vf[8];
+            unpack8(w, vf);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pr[g][it], vf[e], o[g][e]);
+            }
+        }
+        __syncwarp();   // every lane is done with this stage and with pbuf
+
+        // ---- end of a segment (kv head exhausted, or this warp's range ends) ---------------------
+        const bool pair_done = (ci.ck == ci.n - 1);
+        if (pair_done || i == n_local - 1) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                l[g] = warp_sum(l[g]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[g][e] += __shfl_xor_sync(0xffffffffu, o[g][e], 16);
+            }
+            const int pair = ci.b * hkv + ci.h;
+            const long long c0 = (long long)hkv * cum[ci.b] + (long long)ci.h * ci.n;
+            const long long c1 = c0 + ci.n;
+            const int w_first = (int)(((c0 + 1) * TWe - 1) / C);
+            const int w_last = (int)((c1 * TWe - 1) / C);
+            const int nseg = w_last - w_first + 1;
+            __nv_bfloat16* orow = p.out + (int64_t)ci.b * p.out_stride + (ci.h * G) * B200_HEAD_DIM + j * 8;
+            if (nseg == 1) {
+                if (hw == 0) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float inv = 1.f / l[g];
+                        float r[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) r[e] = o[g][e] * inv;
+                        *reinterpret_cast<uint4*>(orow + g * B200_HEAD_DIM) = pack8(r);
+                    }
+                }
+            } else {
+                const int myslot = (gw == w_first) ? TW + pair : gw;
+                float* po = p.part_o + (int64_t)myslot * (G * B200_HEAD_DIM) + j * 8;
+                if (hw == 0) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float4* d4 = reinterpret_cast<float4*>(po + g * B200_HEAD_DIM);
+                        d4[0] = make_float4(o[g][0], o[g][1], o[g][2], o[g][3]);
+                        d4[1] = make_float4(o[g][4], o[g][5], o[g][6], o[g][7]);
+                    }
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        p.part_ml[((int64_t)myslot * G + g) * 2 + 0] = m[g];
+                        p.part_ml[((int64_t)myslot * G + g) * 2 + 1] = l[g];
+                    }
+                }
+                __threadfence();
+                __syncwarp();
+                int old = 0;
+                if (lane == 0) old = atomicAdd(p.counters + pair, 1);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == nseg - 1) {               // last segment in: merge in fixed order
+                    __threadfence();
+                    if (hw == 0) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            float M = -INFINITY;
+                            for (int k = 0; k < nseg; ++k) {
+                                const int sl = k == 0 ? TW + pair : w_first + k;
+                                M = fmaxf(M, __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2));
+                            }
+                            float Ls = 0.f;
+                            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            for (int k = 0; k < nseg; ++k) {
+                                const int sl = k == 0 ? TW + pair : w_first + k;
+                                const float mk = __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2);
+                                const float lk = __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2 + 1);
+                                const float wgt = fast_exp2(mk - M);
+                                Ls = fmaf(lk, wgt, Ls);
+                                const float4* s4 = reinterpret_cast<const float4*>(
+                                    p.part_o + ((int64_t)sl * G + g) * B200_HEAD_DIM + j * 8);
+                                const float4 a = __ldcg(s4), c4 = __ldcg(s4 + 1);
+                                r[0] = fmaf(a.x, wgt, r[0]); r[1] = fmaf(a.y, wgt, r[1]);
+                                r[2] = fmaf(a.z, wgt, r[2]); r[3] = fmaf(a.w, wgt, r[3]);
+                                r[4] = fmaf(c4.x, wgt, r[4]); r[5] = fmaf(c4.y, wgt, r[5]);
+                                r[6] = fmaf(c4.z, wgt, r[6]); r[7] = fmaf(c4.w, wgt, r[7]);
+                            }
+                            const float inv = 1.f / Ls;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) r[e] *= inv;
+                            *reinterpret_cast<uint4*>(orow + g * B200_HEAD_DIM) = pack8(r);
+                        }
+                    }
+                    if (lane == 0) p.counters[pair] = 0;   // leave the workspace clean for the next launch
+                }
+            }
+            seg_start = true;
+        }
+        ci.advance(cum, ctxs, batch, hkv);
+    }
+}
+
+constexpr int kWarps = 8;
+constexpr int kStages = 3;
+
+template <int G>
+int launch_decode(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
+    using L = DecodeSmem<G, kWarps, kStages>;
+    auto kern = paged_decode_kernel<G, kWarps, kStages>;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    kern<<<ctx->sm_count, kWarps * 32, L::kTotal, stream>>>(prm);
+    return b200_launch_status(ctx);
+}
+
+}  // namespace
+
+struct WsLayout {
+    size_t off_ml, off_o, total;
+};
+// [counters: MAX_BATCH*hkv ints -- fixed place whatever the batch, they persist (as zeros) between
+//  launches][part_ml][part_o]; the two scratch regions may move with the batch size.
+static WsLayout ws_layout(int sm_count, int batch, int hkv, int G) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t slots = (size_t)sm_count * kWarps + (size_t)batch * hkv;
+    WsLayout w;
+    size_t off = al((size_t)MAX_BATCH * hkv * sizeof(int));
+    w.off_ml = off;
+    off += al(slots * G * 2 * sizeof(float));
+    w.off_o = off;
+    off += al(slots * G * B200_HEAD_DIM * sizeof(float));
+    w.total = off;
+    return w;
+}
+
+extern "C" size_t b200_decode_workspace_bytes(const b200_ctx* ctx, int max_batch, int num_q_heads) {
+    if (!ctx || ctx->num_kv_heads <= 0 || max_batch <= 0 || num_q_heads % ctx->num_kv_heads) return 0;
+    return ws_layout(ctx->sm_count, max_batch, ctx->num_kv_heads, num_q_heads / ctx->num_kv_heads).total;
+}
+
+extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0,
+                                 const int32_t* block_tables, int bt_stride,
+                                 const int32_t* context_lens, void* out, int64_t out_stride0,
+                                 int batch, int num_q_heads, float scale, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!ctx || !q || !out || !block_tables || !context_lens || !workspace) return B200_EINVAL;
+    if (!ctx->k_base) return B200_ENOTBOUND;
+    if (layer < 0 || layer >= ctx->layers || batch < 0) return B200_EINVAL;
+    if (batch == 0) return B200_OK;
+    if (batch > MAX_BATCH) return B200_EUNSUPPORTED;
+    const int hkv = ctx->num_kv_heads;
+    if (num_q_heads % hkv) return B200_EINVAL;
+    const int G = num_q_heads / hkv;
+    if (G != 1 && G != 2 && G != 4 && G != 8) return B200_EUNSUPPORTED;
+    if ((q_stride0 % 8) || (out_stride0 % 8) || ((uintptr_t)q % 16) || ((uintptr_t)out % 16)) return B200_EINVAL;
+    const WsLayout w = ws_layout(ctx->sm_count, batch, hkv, G);
+    if (workspace_bytes < w.total) return B200_EWORKSPACE;
+
+    DecodeParams prm;
+    prm.q = static_cast<const __nv_bfloat16*>(q);
+    prm.q_stride = q_stride0;
+    prm.out = static_cast<__nv_bfloat16*>(out);
+    prm.out_stride = out_stride0;
+    prm.k_layer = ctx->k_layer(layer);
+    prm.v_layer = ctx->v_layer(layer);
+    prm.block_tables = block_tables;
+    prm.bt_stride = bt_stride;
+    prm.context_lens = context_lens;
+    prm.batch = batch;
+    prm.hkv = hkv;
+    prm.block_shift = ctx->block_shift;
+    prm.scale_log2 = scale * 1.4426950408889634f;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    prm.counters = reinterpret_cast<int*>(ws);
+    prm.part_ml = reinterpret_cast<float*>(ws + w.off_ml);
+    prm.part_o = reinterpret_cast<float*>(ws + w.off_o);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (G) {
+        case 1: return launch_decode<1>(ctx, prm, st);
+        case 2: return launch_decode<2>(ctx, prm, st);
+        case 4: return launch_decode<4>(ctx, prm, st);
+        default: return launch_decode<8>(ctx, prm, st);
+    }
+}

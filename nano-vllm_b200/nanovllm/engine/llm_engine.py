@@ -1,0 +1,165 @@
+"""The engine behind ``LLM`` (reference nanovllm/engine/llm_engine.py:15-90): same public methods
+(``add_request``, ``step``, ``is_finished``, ``generate``, ``exit``), same return shapes.
+
+Tensor parallelism is SPMD: each GPU process owns a full replica of the (deterministic) scheduler
+and its own ModelRunner and executes the same steps in lock-step.  Two ways to get the ranks:
+
+* launched by ``torchrun`` / any launcher that sets RANK, WORLD_SIZE (== tensor_parallel_size),
+  LOCAL_RANK, MASTER_ADDR, MASTER_PORT: every process simply constructs ``LLM(...)`` and calls the
+  same methods (this is how bench.py runs at N > 1);
+* plain ``LLM(path, tensor_parallel_size=N)`` from one process, like the reference
+  (llm_engine.py:24-30): ranks 1..N-1 are spawned and mirror rank 0's API calls, which are broadcast
+  once per call (one message per ``generate``, not one per step).
+"""
+from __future__ import annotations
+
+import atexit
+import os
+from dataclasses import fields
+from time import perf_counter
+
+from ..config import Config
+from ..sampling_params import SamplingParams
+from .model_runner import ModelRunner
+from .scheduler import Scheduler
+from .sequence import Sequence
+
+
+def _free_port() -> int:
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker_main(model: str, kwargs: dict, rank: int, world: int, port: int):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    engine = LLMEngine(model, **kwargs)
+    engine._serve()
+
+
+class LLMEngine:
+    def __init__(self, model: str, **kwargs):
+        names = {f.name for f in fields(Config)}
+        config = Config(model, **{k: v for k, v in kwargs.items() if k in names})   # unknown keys are ignored
+        self.config = config
+        Sequence.block_size = config.kvcache_block_size
+        tp = config.tensor_parallel_size
+        self.rank, self._procs, self._mirrors = 0, [], False
+        if tp > 1:
+            if int(os.environ.get("WORLD_SIZE", "1")) == tp and "RANK" in os.environ:
+                self.rank = int(os.environ["RANK"])                                  # launcher-provided replicas
+            else:
+                import torch.multiprocessing as mp
+                port = _free_port()
+                os.environ.update(RANK="0", LOCAL_RANK="0", WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1",
+                                  MASTER_PORT=str(port))
+                ctx = mp.get_context("spawn")
+                for r in range(1, tp):
+                    p = ctx.Process(target=_worker_main, args=(model, dict(kwargs), r, tp, port), daemon=True)
+                    p.start()
+                    self._procs.append(p)
+                self._mirrors = True
+        self.model_runner = ModelRunner(config, self.rank, None)
+        from transformers import AutoTokenizer
+        self.tokenizer = AutoTokenizer.from_pretrained(config.model, use_fast=True)
+        config.eos = self.tokenizer.eos_token_id if self.tokenizer.eos_token_id is not None else -1
+        self.scheduler = Scheduler(config)            # after the runner: it needs num_kvcache_blocks
+        self._closed = False
+        atexit.register(self.exit)
+
+    # ---- rank-0 -> mirror ranks control channel (spawn mode only) --------------------------
+    def _tell(self, *cmd):
+        if self._mirrors:
+            import torch.distributed as dist
+            dist.broadcast_object_list([cmd], src=0)
+
+    def _serve(self):
+        import torch.distributed as dist
+        while True:
+            box = [None]
+            dist.broadcast_object_list(box, src=0)
+            cmd, *args = box[0]
+            if cmd == "generate":
+                self._generate(*args, use_tqdm=False)
+            elif cmd == "add":
+                self._add_request(*args)
+            elif cmd == "step":
+                self._step()
+            elif cmd == "exit":
+                self._close()
+                return
+
+    # ---- public API ------------------------------------------------------------------------
+    def exit(self):
+        if self._closed:
+            return
+        self._tell("exit")
+        self._close()
+        for p in self._procs:
+            p.join(timeout=30)
+
+    def _close(self):
+        if not self._closed:
+            self._closed = True
+            self.model_runner.call("exit")
+
+    def add_request(self, prompt: str | list[int], sampling_params: SamplingParams):
+        if isinstance(prompt, str):
+            prompt = self.tokenizer.encode(prompt)
+        self._tell("add", prompt, sampling_params)
+        self._add_request(prompt, sampling_params)
+
+    def _add_request(self, prompt: list[int], sampling_params: SamplingParams):
+        self.scheduler.add(Sequence(prompt, sampling_params))
+
+    def step(self):
+        self._tell("step")
+        return self._step()
+
+    def _step(self):
+        seqs, is_prefill = self.scheduler.schedule()
+        num_tokens = sum(s.num_scheduled_tokens for s in seqs) if is_prefill else -len(seqs)
+        token_ids = self.model_runner.call("run", seqs, is_prefill)
+        self.scheduler.postprocess(seqs, token_ids, is_prefill)
+        outputs = [(s.seq_id, s.completion_token_ids) for s in seqs if s.is_finished]
+        return outputs, num_tokens
+
+    def is_finished(self) -> bool:
+        return self.scheduler.is_finished()
+
+    def generate(self, prompts: list[str] | list[list[int]], sampling_params: SamplingParams | list[SamplingParams],
+                 use_tqdm: bool = True) -> list[dict]:
+        prompts = [self.tokenizer.encode(p) if isinstance(p, str) else list(p) for p in prompts]
+        self._tell("generate", prompts, sampling_params)
+        return self._generate(prompts, sampling_params, use_tqdm and self.rank == 0)
+
+    def _generate(self, prompts, sampling_params, use_tqdm: bool):
+        pbar = None
+        if use_tqdm:
+            from tqdm.auto import tqdm
+            pbar = tqdm(total=len(prompts), desc="Generating", dynamic_ncols=True)
+        if not isinstance(sampling_params, list):
+            sampling_params = [sampling_params] * len(prompts)
+        for prompt, sp in zip(prompts, sampling_params):
+            self._add_request(prompt, sp)
+        done: dict[int, list[int]] = {}
+        prefill_tps = decode_tps = 0.0
+        while not self.is_finished():
+            t0 = perf_counter()
+            finished, num_tokens = self._step()
+            dt = perf_counter() - t0
+            if num_tokens > 0:
+                prefill_tps = num_tokens / dt
+            else:
+                decode_tps = -num_tokens / dt
+            for seq_id, toks in finished:
+                done[seq_id] = toks
+            if pbar is not None:
+                pbar.set_postfix({"Prefill": f"{int(prefill_tps)}tok/s", "Decode": f"{int(decode_tps)}tok/s"})
+                pbar.update(len(finished))
+        if pbar is not None:
+            pbar.close()
+        ordered = [done[k] for k in sorted(done)]
+        return [{"text": self.tokenizer.decode(t), "token_ids": t} for t in ordered]

@@ -1,0 +1,367 @@
+"""Per-GPU executor: device setup, KV-cache sizing/binding, step marshalling, CUDA graphs, sampling.
+
+Same contract as the reference's ModelRunner (nanovllm/engine/model_runner.py:15-257):
+``ModelRunner(config, rank, event)`` sets ``config.num_kvcache_blocks``; ``call("run", seqs,
+is_prefill) -> list[int]`` returns one token id per sequence; one process per GPU, one thread,
+everything on the current stream, one device->host sync per step.
+
+B200-first differences (DESIGN.md "runner"):
+* per-step metadata travels in ONE pinned staging buffer and ONE host->device copy into static
+  device buffers (the reference builds seven pinned tensors and seven copies per step);
+* the decode graph contains the whole step: embedding ... final norm, LM head, sampling and (under
+  tensor parallelism) the all-reduces; the reference leaves logits and sampling outside;
+* tensor-parallel ranks are SPMD replicas: every rank runs the same (deterministic) scheduler and
+  this runner in lock-step, so there is no per-step RPC (the reference pickles the batch into shared
+  memory every step, model_runner.py:61-89); ranks agree on the sampled tokens through the
+  all-reduce(MAX) of packed (score, token) keys that replaces the reference's logits gather.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import _native as nat
+from .. import ops
+from ..config import Config
+from ..models.qwen3 import Qwen3ForCausalLM
+from ..utils.context import reset_context, set_context
+from ..utils.loader import load_model
+from .sequence import Sequence
+
+_ALIGN = 64
+
+
+def _align(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class _Staging:
+    """A pinned host byte buffer mirrored by a device byte buffer; regions are typed views."""
+
+    def __init__(self, nbytes: int):
+        self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        self.dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self.host_np = self.host.numpy()
+
+    def views(self, off: int, count: int, np_dtype, torch_dtype):
+        nbytes = count * np.dtype(np_dtype).itemsize
+        h = self.host_np[off:off + nbytes].view(np_dtype)
+        d = self.dev[off:off + nbytes].view(torch_dtype)
+        return h, d
+
+    def upload(self, nbytes: int):
+        self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
+
+
+class ModelRunner:
+    def __init__(self, config: Config, rank: int = 0, event=None, sample_seed: int = 0):
+        self.config = config
+        hf = config.hf_config
+        self.block_size = config.kvcache_block_size
+        self.enforce_eager = config.enforce_eager
+        self.world_size = config.tensor_parallel_size
+        self.rank = rank
+        self.event = event
+        self.sample_seed = sample_seed
+        self.sample_step = 0
+
+        if not torch.cuda.is_available():
+            raise nat.B200Error("ModelRunner needs a CUDA device: the B200 path has no CPU fallback")
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        self.device = torch.device("cuda", local)
+        self._own_pg = False
+        if self.world_size > 1 and not dist.is_initialized():
+            addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+            port = os.environ.get("MASTER_PORT", "2333")
+            dist.init_process_group("nccl", init_method=f"tcp://{addr}:{port}", world_size=self.world_size,
+                                    rank=rank, device_id=self.device)
+            self._own_pg = True
+        if self.world_size > 1:
+            assert dist.get_world_size() == self.world_size, "tensor_parallel_size must equal the process-group size"
+        self.native = nat.handle(local)
+
+        self.model = Qwen3ForCausalLM(hf, rank, self.world_size, self.device, max_position=hf.max_position_embeddings)
+        load_model(self.model, config.model, allow_random=bool(os.environ.get("NANOVLLM_ALLOW_RANDOM_INIT")))
+        self.vocab_offset = rank * self.model.vocab_shard
+
+        if config.max_num_seqs > 1024:
+            raise ValueError("max_num_seqs > 1024 is not supported by the decode kernel's per-launch batch table")
+        self.cap_bs = config.max_num_seqs                    # rows of the static decode buffers
+        self.max_bs = min(config.max_num_seqs, 512)          # largest captured graph (model_runner.py:226)
+        self.max_blocks = (config.max_model_len + self.block_size - 1) // self.block_size
+        self._init_staging()
+        self.warmup_model()
+        self.allocate_kv_cache()
+        self.graphs: dict[int, torch.cuda.CUDAGraph] = {}
+        self.graph_bs: list[int] = []
+        self.graph_pool = None
+        if not self.enforce_eager:
+            self.capture_cudagraph()
+
+    # ---- reference-compatible dispatch (model_runner.py:85-89) ------------------------------
+    def call(self, method_name: str, *args):
+        return getattr(self, method_name)(*args)
+
+    def exit(self):
+        self.graphs.clear()
+        self.graph_pool = None
+        torch.cuda.synchronize()
+        if self._own_pg and dist.is_initialized():
+            dist.destroy_process_group()
+
+    # ---- staging layout -----------------------------------------------------------------------
+    def _init_staging(self):
+        cfg = self.config
+        T = max(cfg.max_num_batched_tokens, self.cap_bs)
+        S = self.cap_bs
+        W = self.max_blocks
+        # decode region: static offsets (they are baked into the CUDA graphs)
+        o = 0
+        self.d_off = {}
+        mb = self.cap_bs
+        for name, count, size in (("step", 1, 8), ("ids", mb, 8), ("pos", mb, 8), ("slot", mb, 4), ("ctx", mb, 4),
+                                  ("temp", mb, 4), ("bt", mb * W, 4)):
+            self.d_off[name] = o
+            o = _align(o + count * size)
+        self.d_bytes = o
+        prefill_bytes = _align(8) + 2 * _align(T * 8) + _align(T * 4) + 2 * _align((S + 1) * 4) + _align(S * 4) + _align(S * W * 4)
+        self.stage = _Staging(self.d_bytes)
+        self.pstage = _Staging(prefill_bytes)
+        st = self.stage
+        self.h_step, self.g_step = st.views(self.d_off["step"], 1, np.int64, torch.int64)
+        self.h_ids, self.g_ids = st.views(self.d_off["ids"], mb, np.int64, torch.int64)
+        self.h_pos, self.g_pos = st.views(self.d_off["pos"], mb, np.int64, torch.int64)
+        self.h_slot, self.g_slot = st.views(self.d_off["slot"], mb, np.int32, torch.int32)
+        self.h_ctx, self.g_ctx = st.views(self.d_off["ctx"], mb, np.int32, torch.int32)
+        self.h_temp, self.g_temp = st.views(self.d_off["temp"], mb, np.float32, torch.float32)
+        h_bt, g_bt = st.views(self.d_off["bt"], mb * W, np.int32, torch.int32)
+        self.h_bt, self.g_bt = h_bt.reshape(mb, W), g_bt.view(mb, W)
+        self.h_bt[:] = 0
+        self.g_bt.zero_()
+        self.g_tokens = torch.zeros(S, dtype=torch.int64, device="cuda")
+        self.g_keys = torch.zeros(S, dtype=torch.int64, device="cuda")
+        self.h_tokens = torch.empty(S, dtype=torch.int64, pin_memory=True)
+        self.h_tokens_np = self.h_tokens.numpy()
+        self.h2d_bytes_last = 0
+        self.d2h_bytes_last = 0
+
+    # ---- init-time passes -----------------------------------------------------------------------
+    def warmup_model(self):
+        """One maximum-size prefill without a cache, to find the activation peak (model_runner.py:91-101)."""
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        cfg = self.config
+        seq_len = min(cfg.max_num_batched_tokens, cfg.max_model_len)
+        num_seqs = min(cfg.max_num_batched_tokens // seq_len, cfg.max_num_seqs)
+        seqs = [Sequence([0] * seq_len) for _ in range(num_seqs)]
+        for s in seqs:
+            s.num_scheduled_tokens = seq_len
+        self.run(seqs, True)
+        torch.cuda.empty_cache()
+
+    def kv_block_bytes(self) -> int:
+        hf = self.config.hf_config
+        return 2 * hf.num_hidden_layers * self.block_size * self.model.num_kv_heads * self.model.head_dim * 2
+
+    def allocate_kv_cache(self):
+        """Size the cache from free memory with the reference's formula (model_runner.py:103-113), allocate
+        it head-major, bind it to the library and hand each attention operator its layer views (116-121)."""
+        cfg = self.config
+        hf = cfg.hf_config
+        if cfg.num_kvcache_blocks is None or cfg.num_kvcache_blocks <= 0:
+            free, total = torch.cuda.mem_get_info()
+            used = total - free
+            stats = torch.cuda.memory_stats()
+            peak, current = stats["allocated_bytes.all.peak"], stats["allocated_bytes.all.current"]
+            nblk = int(total * cfg.gpu_memory_utilization - used - peak + current) // self.kv_block_bytes()
+            if self.world_size > 1:                      # replicas must agree on the block count
+                t = torch.tensor([nblk], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                nblk = int(t.item())
+            cfg.num_kvcache_blocks = nblk
+        if cfg.num_kvcache_blocks <= 0:
+            raise RuntimeError("not enough GPU memory for a single KV-cache block")
+        m = self.model
+        self.kv_cache = torch.zeros(ops.kv_cache_shape(hf.num_hidden_layers, cfg.num_kvcache_blocks, m.num_kv_heads,
+                                                       self.block_size, m.head_dim), dtype=torch.bfloat16, device="cuda")
+        ops.bind_kv_cache(self.kv_cache)
+        ops.ensure_workspace(self.cap_bs, m.num_heads)
+        layer_id = 0
+        for module in m.modules():
+            if hasattr(module, "k_cache") and hasattr(module, "v_cache"):
+                module.k_cache = self.kv_cache[0, layer_id]
+                module.v_cache = self.kv_cache[1, layer_id]
+                module.layer_id = layer_id
+                layer_id += 1
+
+    # ---- step marshalling (host integer work; must match the reference bit for bit) ------------
+    def prepare_block_tables(self, seqs: list[Sequence]) -> np.ndarray:
+        """[len(seqs), max blocks in batch] int32, right-padded with -1 (model_runner.py:123-127)."""
+        width = max(len(s.block_table) for s in seqs)
+        bt = np.full((len(seqs), width), -1, dtype=np.int32)
+        for i, s in enumerate(seqs):
+            bt[i, :len(s.block_table)] = s.block_table
+        return bt
+
+    def prefill_arrays(self, seqs: list[Sequence]) -> dict:
+        """Host arrays of a prefill step (model_runner.py:129-170): the scheduled token window of each
+        sequence, its positions, cumulative q/k lengths, one cache slot per new token, and block tables
+        only when some K/V comes from the cache (prefix hit or a later prompt chunk)."""
+        bs = self.block_size
+        ids, pos, slots = [], [], []
+        cu_q, cu_k = [0], [0]
+        max_q = max_k = 0
+        for s in seqs:
+            start = s.num_cached_tokens
+            end = start + s.num_scheduled_tokens
+            ids.append(np.asarray(s.token_ids[start:end], dtype=np.int64))
+            p = np.arange(start, end, dtype=np.int64)
+            pos.append(p)
+            cu_q.append(cu_q[-1] + (end - start))
+            cu_k.append(cu_k[-1] + end)
+            max_q, max_k = max(max_q, end - start), max(max_k, end)
+            if s.block_table:                                # absent only in the warm-up pass
+                table = np.asarray(s.block_table, dtype=np.int64)
+                slots.append((table[p // bs] * bs + p % bs).astype(np.int32))
+        out = dict(input_ids=np.concatenate(ids) if ids else np.zeros(0, np.int64),
+                   positions=np.concatenate(pos) if pos else np.zeros(0, np.int64),
+                   cu_seqlens_q=np.asarray(cu_q, dtype=np.int32), cu_seqlens_k=np.asarray(cu_k, dtype=np.int32),
+                   max_seqlen_q=max_q, max_seqlen_k=max_k,
+                   slot_mapping=np.concatenate(slots) if slots else np.zeros(0, np.int32), block_tables=None)
+        if cu_k[-1] > cu_q[-1]:
+            out["block_tables"] = self.prepare_block_tables(seqs)
+        return out
+
+    def decode_arrays(self, seqs: list[Sequence]) -> dict:
+        """Host arrays of a decode step (model_runner.py:172-188)."""
+        bs = self.block_size
+        n = len(seqs)
+        ids = np.fromiter((s.last_token for s in seqs), dtype=np.int64, count=n)
+        lens = np.fromiter((s.num_tokens for s in seqs), dtype=np.int64, count=n)
+        last_blk = np.fromiter((s.block_table[-1] for s in seqs), dtype=np.int64, count=n)
+        # last_block_num_tokens = len - (num_blocks - 1) * bs, so the slot of the newest token is:
+        slots = last_blk * bs + (lens - 1) % bs
+        return dict(input_ids=ids, positions=lens - 1, slot_mapping=slots.astype(np.int32),
+                    context_lens=lens.astype(np.int32), block_tables=self.prepare_block_tables(seqs))
+
+    def prepare_prefill(self, seqs: list[Sequence]):
+        a = self.prefill_arrays(seqs)
+        st = self.pstage
+        off = 0
+        views = {}
+        plan = [("step", np.asarray([self.sample_step], np.int64), torch.int64),
+                ("input_ids", a["input_ids"], torch.int64), ("positions", a["positions"], torch.int64),
+                ("slot_mapping", a["slot_mapping"], torch.int32),
+                ("cu_seqlens_q", a["cu_seqlens_q"], torch.int32), ("cu_seqlens_k", a["cu_seqlens_k"], torch.int32),
+                ("temps", np.fromiter((s.temperature for s in seqs), dtype=np.float32, count=len(seqs)), torch.float32)]
+        if a["block_tables"] is not None:
+            plan.append(("block_tables", np.ascontiguousarray(a["block_tables"]).reshape(-1), torch.int32))
+        for name, arr, tdt in plan:
+            h, d = st.views(off, arr.size, arr.dtype, tdt)
+            h[:] = arr
+            views[name] = d
+            off = _align(off + arr.nbytes)
+        st.upload(off)
+        self.h2d_bytes_last = off
+        bt = views.get("block_tables")
+        if bt is not None:
+            bt = bt.view(len(seqs), -1)
+        slot = views["slot_mapping"] if a["slot_mapping"].size else None
+        set_context(True, views["cu_seqlens_q"], views["cu_seqlens_k"], a["max_seqlen_q"], a["max_seqlen_k"],
+                    slot, None, bt)
+        return views["input_ids"], views["positions"], views["temps"], views["step"]
+
+    def prepare_decode(self, seqs: list[Sequence], padded: int):
+        """Fill the static decode buffers for len(seqs) live rows padded to `padded` rows and upload them."""
+        a = self.decode_arrays(seqs)
+        n = len(seqs)
+        self.h_step[0] = self.sample_step
+        self.h_ids[:n] = a["input_ids"]
+        self.h_pos[:n] = a["positions"]
+        self.h_slot[:n] = a["slot_mapping"]
+        self.h_ctx[:n] = a["context_lens"]
+        self.h_temp[:n] = np.fromiter((s.temperature for s in seqs), dtype=np.float32, count=n)
+        if padded > n:                                       # graph padding rows (model_runner.py:206-208)
+            self.h_ids[n:padded] = 0
+            self.h_pos[n:padded] = 0
+            self.h_slot[n:padded] = -1
+            self.h_ctx[n:padded] = 0
+            self.h_temp[n:padded] = 0
+        bt = a["block_tables"]
+        self.h_bt[:n, :bt.shape[1]] = bt
+        W = self.max_blocks
+        nbytes = self.d_off["bt"] + padded * W * 4
+        self.stage.upload(nbytes)
+        self.h2d_bytes_last = nbytes
+        set_context(False, slot_mapping=self.g_slot[:padded], context_lens=self.g_ctx[:padded],
+                    block_tables=self.g_bt[:padded])
+
+    # ---- model + sampling -------------------------------------------------------------------------
+    def _forward_and_sample(self, input_ids, positions, temps, step_dev, rows: int):
+        """hidden -> shard logits -> sampled token ids in self.g_tokens[:rows] (all enqueued, no sync)."""
+        hidden = self.model(input_ids, positions)
+        logits = self.model.compute_logits(hidden)
+        if self.world_size == 1:
+            ops.sample(logits, temps, self.sample_seed, 0, out=self.g_tokens[:rows], step_dev=step_dev)
+        else:
+            keys = self.g_keys[:rows]
+            ops.sample(logits, temps, self.sample_seed, 0, out=self.g_tokens[:rows], index_offset=self.vocab_offset,
+                       out_keys=keys, step_dev=step_dev)
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+            self.g_tokens[:rows].copy_(ops.tokens_from_keys(keys))
+
+    @torch.inference_mode()
+    def run(self, seqs: list[Sequence], is_prefill: bool) -> list[int]:
+        n = len(seqs)
+        self.sample_step += 1
+        if is_prefill:
+            ids, pos, temps, step_dev = self.prepare_prefill(seqs)
+            self._forward_and_sample(ids, pos, temps, step_dev, n)
+        else:
+            use_graph = (not self.enforce_eager) and n <= self.max_bs and bool(self.graphs)
+            padded = next(b for b in self.graph_bs if b >= n) if use_graph else n
+            if n > self.cap_bs:
+                raise RuntimeError(f"decode batch {n} exceeds max_num_seqs = {self.cap_bs}")
+            self.prepare_decode(seqs, padded)
+            if use_graph:
+                self.graphs[padded].replay()
+            else:
+                self._forward_and_sample(self.g_ids[:n], self.g_pos[:n], self.g_temp[:n], self.g_step, n)
+        self.h_tokens[:n].copy_(self.g_tokens[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()            # the step's only host sync
+        self.d2h_bytes_last = n * 8
+        reset_context()
+        return self.h_tokens_np[:n].tolist()
+
+    @torch.inference_mode()
+    def capture_cudagraph(self):
+        """One graph per batch-size bucket over the static buffers, largest first so they share one pool
+        (model_runner.py:222-257; same bucket list)."""
+        max_bs = self.max_bs
+        self.graph_bs = [b for b in (1, 2, 4, 8) if b <= max_bs] + list(range(16, max_bs + 1, 16))
+        if max_bs not in self.graph_bs:
+            self.graph_bs.append(max_bs)
+        self.h_ctx[:] = 0
+        self.h_slot[:] = -1
+        self.h_ids[:] = 0
+        self.h_pos[:] = 0
+        self.h_temp[:] = 0
+        self.stage.upload(self.d_bytes)
+        torch.cuda.synchronize()
+        for bs in reversed(self.graph_bs):
+            set_context(False, slot_mapping=self.g_slot[:bs], context_lens=self.g_ctx[:bs], block_tables=self.g_bt[:bs])
+            args = (self.g_ids[:bs], self.g_pos[:bs], self.g_temp[:bs], self.g_step, bs)
+            self._forward_and_sample(*args)                  # warm-up outside capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, self.graph_pool):
+                self._forward_and_sample(*args)
+            if self.graph_pool is None:
+                self.graph_pool = graph.pool()
+            self.graphs[bs] = graph
+            torch.cuda.synchronize()
+            reset_context()

@@ -1,0 +1,180 @@
+"""Qwen3 dense decoder on the B200 kernels (reference nanovllm/models/qwen3.py:14-216).
+
+Same architecture and the same rounding points as the reference's GPU path: GQA with per-head q/k
+RMSNorm before NeoX RoPE, SwiGLU MLP, fused residual-add + RMSNorm; bf16 tensors between ops, fp32
+inside them.  Per layer and per step this issues
+
+    add_rmsnorm -> qkv GEMM -> [q/k-norm + RoPE + KV scatter] -> paged attention -> o GEMM (+all-reduce)
+    -> add_rmsnorm -> gate_up GEMM -> silu*mul -> down GEMM (+all-reduce)
+
+GEMMs are library calls (cuBLAS through ``F.linear``, as in the reference, linear.py:51,73,153);
+everything else is one hand-written kernel from libb200attn.  Tensor parallelism shards heads and
+MLP columns exactly like the reference's *ParallelLinear classes (linear.py:54-156) and all-reduces
+after o_proj and down_proj only; the embedding table is replicated and the LM head stays
+vocab-sharded with a (max, argmax) combine instead of a logits gather (embed_head.py:56-66).
+
+This is a plain object, not an nn.Module tree: weights are named tensors, ``forward`` is a flat
+list of launches, which is what gets captured into the decode CUDA graphs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .. import ops
+from ..layers.attention import Attention
+from ..layers.rotary_embedding import build_cos_sin
+from ..utils.context import get_context
+
+
+@dataclass
+class LayerWeights:
+    qkv: torch.Tensor         # [(Hq + 2 Hkv) * D / tp, hidden]
+    o: torch.Tensor           # [hidden, Hq * D / tp]
+    gate_up: torch.Tensor     # [2 * I / tp, hidden]
+    down: torch.Tensor        # [hidden, I / tp]
+    ln1: torch.Tensor
+    ln2: torch.Tensor
+    q_norm: torch.Tensor
+    k_norm: torch.Tensor
+
+
+class Qwen3ForCausalLM:
+    # HF checkpoint name -> (packed parameter, shard id), as in the reference (qwen3.py:187-193)
+    packed_modules_mapping = {
+        "q_proj": ("qkv_proj", "q"), "k_proj": ("qkv_proj", "k"), "v_proj": ("qkv_proj", "v"),
+        "gate_proj": ("gate_up_proj", 0), "up_proj": ("gate_up_proj", 1),
+    }
+
+    def __init__(self, hf_config, tp_rank: int = 0, tp_size: int = 1, device="cuda", max_position: int | None = None):
+        c = hf_config
+        self.cfg = c
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.device = torch.device(device)
+        self.hidden = c.hidden_size
+        self.head_dim = getattr(c, "head_dim", None) or c.hidden_size // c.num_attention_heads
+        assert c.num_attention_heads % tp_size == 0 and c.num_key_value_heads % tp_size == 0
+        assert c.vocab_size % tp_size == 0 and c.intermediate_size % tp_size == 0
+        self.num_heads = c.num_attention_heads // tp_size
+        self.num_kv_heads = c.num_key_value_heads // tp_size
+        self.inter = c.intermediate_size // tp_size
+        self.vocab_shard = c.vocab_size // tp_size
+        self.eps = c.rms_norm_eps
+        self.q_size = self.num_heads * self.head_dim
+        self.kv_size = self.num_kv_heads * self.head_dim
+        self.tie = bool(getattr(c, "tie_word_embeddings", False))
+        if getattr(c, "attention_bias", False):
+            raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
+        theta = getattr(c, "rope_theta", 1000000.0)
+        scaling = getattr(c, "rope_scaling", None) or getattr(c, "rope_parameters", None)
+        if isinstance(scaling, dict):
+            theta = scaling.get("rope_theta", theta)
+        self.rope_theta = float(theta)
+        self.cos_sin = build_cos_sin(self.head_dim, max_position or c.max_position_embeddings, self.rope_theta, self.device)
+
+        dt, dev = torch.bfloat16, self.device
+        e = lambda *s: torch.empty(*s, dtype=dt, device=dev)
+        self.embed = e(c.vocab_size, self.hidden)                       # replicated
+        self.lm_head = (self.embed[tp_rank * self.vocab_shard:(tp_rank + 1) * self.vocab_shard]
+                        if self.tie else e(self.vocab_shard, self.hidden))
+        self.norm = e(self.hidden)
+        self.layers = [LayerWeights(e(self.q_size + 2 * self.kv_size, self.hidden), e(self.hidden, self.q_size),
+                                    e(2 * self.inter, self.hidden), e(self.hidden, self.inter),
+                                    e(self.hidden), e(self.hidden), e(self.head_dim), e(self.head_dim))
+                       for _ in range(c.num_hidden_layers)]
+        scale = self.head_dim ** -0.5
+        self.attn = [Attention(self.num_heads, self.head_dim, scale, self.num_kv_heads) for _ in self.layers]
+        for i, a in enumerate(self.attn):
+            a.layer_id = i
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_hf_tensor(self, name: str, w: torch.Tensor) -> None:
+        """Place one HF-named checkpoint tensor, slicing this rank's shard (linear.py:65-70,87-93,114-128,142-150)."""
+        r, n = self.tp_rank, self.tp_size
+        if name == "model.embed_tokens.weight":
+            self.embed.copy_(w); return
+        if name == "lm_head.weight":
+            if not self.tie:
+                self.lm_head.copy_(w.chunk(n, 0)[r])
+            return
+        if name == "model.norm.weight":
+            self.norm.copy_(w); return
+        parts = name.split(".")
+        assert parts[0] == "model" and parts[1] == "layers", name
+        L = self.layers[int(parts[2])]
+        leaf = ".".join(parts[3:-1])
+        if leaf == "self_attn.q_proj":
+            L.qkv[:self.q_size].copy_(w.chunk(n, 0)[r])
+        elif leaf == "self_attn.k_proj":
+            L.qkv[self.q_size:self.q_size + self.kv_size].copy_(w.chunk(n, 0)[r])
+        elif leaf == "self_attn.v_proj":
+            L.qkv[self.q_size + self.kv_size:].copy_(w.chunk(n, 0)[r])
+        elif leaf == "self_attn.o_proj":
+            L.o.copy_(w.chunk(n, 1)[r])
+        elif leaf == "mlp.gate_proj":
+            L.gate_up[:self.inter].copy_(w.chunk(n, 0)[r])
+        elif leaf == "mlp.up_proj":
+            L.gate_up[self.inter:].copy_(w.chunk(n, 0)[r])
+        elif leaf == "mlp.down_proj":
+            L.down.copy_(w.chunk(n, 1)[r])
+        elif leaf == "input_layernorm":
+            L.ln1.copy_(w)
+        elif leaf == "post_attention_layernorm":
+            L.ln2.copy_(w)
+        elif leaf == "self_attn.q_norm":
+            L.q_norm.copy_(w)
+        elif leaf == "self_attn.k_norm":
+            L.k_norm.copy_(w)
+        else:
+            raise KeyError(f"unexpected checkpoint tensor {name}")
+
+    def modules(self):
+        """The attention operators, in layer order (what allocate_kv_cache walks, model_runner.py:116-121)."""
+        return iter(self.attn)
+
+    # ---- forward -------------------------------------------------------------------------------
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.tp_size > 1:
+            dist.all_reduce(t)
+        return t
+
+    @torch.inference_mode()
+    def forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        ctx = get_context()
+        eps, hq, hkv, d = self.eps, self.num_heads, self.num_kv_heads, self.head_dim
+        h = ops.embedding(input_ids, self.embed)
+        residual = None
+        for li, L in enumerate(self.layers):
+            attn = self.attn[li]
+            if residual is None:
+                residual, x = h, ops.rmsnorm(h, L.ln1, eps)
+            else:
+                x, residual = ops.add_rmsnorm(h, residual, L.ln1, eps)
+            qkv = F.linear(x, L.qkv)
+            cached = attn.k_cache.numel() > 0
+            ops.qknorm_rope_store(li, qkv, hq, hkv, positions, L.q_norm, L.k_norm, self.cos_sin, eps,
+                                  ctx.slot_mapping if cached else None)
+            t = qkv.shape[0]
+            q = qkv[:, :self.q_size].view(t, hq, d)
+            k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
+            v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
+            o = attn(q, k, v, kv_stored=True)
+            h = self._all_reduce(F.linear(o.reshape(t, self.q_size), L.o))
+            x, residual = ops.add_rmsnorm(h, residual, L.ln2, eps)
+            h = self._all_reduce(F.linear(ops.silu_mul(F.linear(x, L.gate_up)), L.down))
+        x, _ = ops.add_rmsnorm(h, residual, self.norm, eps)
+        return x
+
+    __call__ = forward
+
+    @torch.inference_mode()
+    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
+        """Logits of this rank's vocab shard for the last token of every sequence (embed_head.py:56-61)."""
+        ctx = get_context()
+        if ctx.is_prefill:
+            last = (ctx.cu_seqlens_q[1:] - 1).to(torch.long)
+            hidden = hidden.index_select(0, last)
+        return F.linear(hidden, self.lm_head)
