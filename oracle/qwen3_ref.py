@@ -69,6 +69,46 @@ def rope_table(head_dim: int, max_pos: int, theta: float) -> torch.Tensor:
     return torch.cat((ang.cos(), ang.sin()), dim=-1)
 
 
+# ---- the reference's elementwise ops as free functions (used by the class below and by kernel tests) ----
+def rmsnorm_ref(x, weight, eps, rounding="fused"):
+    """RMSNorm.rms_forward, layers/layernorm.py:16-26."""
+    dt = x.dtype
+    xf = x.float()
+    var = xf.pow(2).mean(dim=-1, keepdim=True)
+    xf = xf * torch.rsqrt(var + eps)
+    if rounding == "eager":                              # layernorm.py:25: x.to(bf16).mul_(weight)
+        return xf.to(dt).mul_(weight)
+    return (xf * weight.float()).to(dt)
+
+
+def add_rmsnorm_ref(x, residual, weight, eps, rounding="fused"):
+    """RMSNorm.add_rms_forward, layers/layernorm.py:28-40 -> (normed, new_residual)."""
+    dt = x.dtype
+    xf = x.float() + residual.float()
+    new_residual = xf.to(dt)
+    var = xf.pow(2).mean(dim=-1, keepdim=True)
+    xf = xf * torch.rsqrt(var + eps)
+    if rounding == "eager":
+        return xf.to(dt).mul_(weight), new_residual
+    return (xf * weight.float()).to(dt), new_residual
+
+
+def rope_ref(cos_sin, positions, x):
+    """RotaryEmbedding.forward / apply_rotary_emb, layers/rotary_embedding.py:6-14,37-48.  x: [T, H, D]."""
+    cs = cos_sin[positions].unsqueeze(1)
+    cos, sin = cs.chunk(2, dim=-1)
+    x1, x2 = torch.chunk(x.float(), 2, dim=-1)
+    return torch.cat((x1 * cos - x2 * sin, x2 * cos + x1 * sin), dim=-1).to(x.dtype)
+
+
+def silu_mul_ref(gate_up, rounding="fused"):
+    """SiluAndMul.forward, layers/activation.py:8-11."""
+    g, u = gate_up.chunk(2, -1)
+    if rounding == "eager":
+        return F.silu(g) * u
+    return (F.silu(g.float()) * u.float()).to(gate_up.dtype)
+
+
 class Qwen3Ref:
     def __init__(self, dims: RefDims, weights: dict, rounding: str = "fused", max_pos: int | None = None,
                  p_dtype=None):
@@ -95,37 +135,17 @@ class Qwen3Ref:
         self.scale = dims.head_dim ** -0.5
 
     # ---- elementwise pieces ------------------------------------------------
-    def _norm_out(self, xf, weight, dt):
-        if self.rounding == "eager":                     # layernorm.py:25 / :39
-            return xf.to(dt).mul_(weight)
-        return (xf * weight.float()).to(dt)
-
     def rmsnorm(self, x, weight):
-        dt = x.dtype
-        xf = x.float()
-        var = xf.pow(2).mean(dim=-1, keepdim=True)
-        xf = xf * torch.rsqrt(var + self.d.rms_norm_eps)
-        return self._norm_out(xf, weight, dt)
+        return rmsnorm_ref(x, weight, self.d.rms_norm_eps, self.rounding)
 
     def add_rmsnorm(self, x, residual, weight):
-        dt = x.dtype
-        xf = x.float() + residual.float()
-        new_residual = xf.to(dt)
-        var = xf.pow(2).mean(dim=-1, keepdim=True)
-        xf = xf * torch.rsqrt(var + self.d.rms_norm_eps)
-        return self._norm_out(xf, weight, dt), new_residual
+        return add_rmsnorm_ref(x, residual, weight, self.d.rms_norm_eps, self.rounding)
 
     def rope(self, positions, x):
-        cs = self.cos_sin[positions].unsqueeze(1)
-        cos, sin = cs.chunk(2, dim=-1)
-        x1, x2 = torch.chunk(x.float(), 2, dim=-1)
-        return torch.cat((x1 * cos - x2 * sin, x2 * cos + x1 * sin), dim=-1).to(x.dtype)
+        return rope_ref(self.cos_sin, positions, x)
 
     def silu_mul(self, gate_up):
-        g, u = gate_up.chunk(2, -1)
-        if self.rounding == "eager":                     # activation.py:10-11
-            return F.silu(g) * u
-        return (F.silu(g.float()) * u.float()).to(gate_up.dtype)
+        return silu_mul_ref(gate_up, self.rounding)
 
     # ---- model -------------------------------------------------------------
     def forward(self, input_ids, positions, ctx, kv_caches):
