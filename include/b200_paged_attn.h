@@ -68,7 +68,8 @@ int b200_kv_bind(b200_ctx* ctx, void* k_base, void* v_base, int layers, int64_t 
                  int block_size, int num_kv_heads, int head_dim);
 
 /* Bytes of scratch b200_paged_decode needs for batches up to max_batch with num_q_heads query
- * heads.  The caller zero-fills it once; the kernel leaves its counters zeroed. */
+ * heads.  The caller zero-fills it once (and again after a b200_kv_bind that changes num_kv_heads: the
+ * layout depends on it); every launch leaves its counters zeroed. */
 size_t b200_decode_workspace_bytes(const b200_ctx* ctx, int max_batch, int num_q_heads);
 
 /* ---- the attention operator (layers/attention.py) -------------------------------------- */

@@ -39,6 +39,7 @@ def bind_kv_cache(kv_cache: torch.Tensor):
     _, layers, nblk, hkv, bs, d = kv_cache.shape
     nat.check(h.lib.b200_kv_bind(h.ptr, kv_cache[0].data_ptr(), kv_cache[1].data_ptr(), layers, nblk, bs, hkv, d), h.ptr)
     h.kv = kv_cache
+    h.workspace = None          # its layout depends on the head count: start again from zeros
     return h
 
 
