@@ -67,6 +67,8 @@ class ModelRunner:
         self.event = event
         self.sample_seed = sample_seed
         self.sample_step = 0
+        self._prof = None
+        self.graph_kernels: dict[int, int] = {}
 
         if not torch.cuda.is_available():
             raise nat.B200Error("ModelRunner needs a CUDA device: the B200 path has no CPU fallback")
@@ -101,6 +103,17 @@ class ModelRunner:
         self.graph_pool = None
         if not self.enforce_eager:
             self.capture_cudagraph()
+
+    # ---- measurement hooks (bench.py) ----------------------------------------------------------
+    def begin_profile(self):
+        """Record a CUDA-event pair around every step's GPU work until end_profile()."""
+        self._prof = dict(events=[], h2d=0, d2h=0, steps=0, launches0=ops.LAUNCHES[0])
+
+    def end_profile(self) -> dict:
+        torch.cuda.synchronize()
+        p, self._prof = self._prof, None
+        return dict(device_ms=sum(a.elapsed_time(b) for a, b in p["events"]), h2d_bytes=p["h2d"], d2h_bytes=p["d2h"],
+                    engine_steps=p["steps"], kernel_launches=ops.LAUNCHES[0] - p["launches0"])
 
     # ---- reference-compatible dispatch (model_runner.py:85-89) ------------------------------
     def call(self, method_name: str, *args):
@@ -318,8 +331,12 @@ class ModelRunner:
     def run(self, seqs: list[Sequence], is_prefill: bool) -> list[int]:
         n = len(seqs)
         self.sample_step += 1
+        prof = self._prof
         if is_prefill:
             ids, pos, temps, step_dev = self.prepare_prefill(seqs)
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             self._forward_and_sample(ids, pos, temps, step_dev, n)
         else:
             use_graph = (not self.enforce_eager) and n <= self.max_bs and bool(self.graphs)
@@ -327,13 +344,25 @@ class ModelRunner:
             if n > self.cap_bs:
                 raise RuntimeError(f"decode batch {n} exceeds max_num_seqs = {self.cap_bs}")
             self.prepare_decode(seqs, padded)
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             if use_graph:
                 self.graphs[padded].replay()
+                ops.LAUNCHES[0] += self.graph_kernels[padded]
             else:
                 self._forward_and_sample(self.g_ids[:n], self.g_pos[:n], self.g_temp[:n], self.g_step, n)
+        if prof is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
         self.h_tokens[:n].copy_(self.g_tokens[:n], non_blocking=True)
         torch.cuda.current_stream().synchronize()            # the step's only host sync
         self.d2h_bytes_last = n * 8
+        if prof is not None:
+            prof["events"].append((ev0, ev1))
+            prof["h2d"] += self.h2d_bytes_last
+            prof["d2h"] += self.d2h_bytes_last
+            prof["steps"] += 1
         reset_context()
         return self.h_tokens_np[:n].tolist()
 
@@ -358,8 +387,10 @@ class ModelRunner:
             self._forward_and_sample(*args)                  # warm-up outside capture
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            before = ops.LAUNCHES[0]
             with torch.cuda.graph(graph, self.graph_pool):
                 self._forward_and_sample(*args)
+            self.graph_kernels[bs] = ops.LAUNCHES[0] - before
             if self.graph_pool is None:
                 self.graph_pool = graph.pool()
             self.graphs[bs] = graph

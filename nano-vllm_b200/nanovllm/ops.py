@@ -10,7 +10,15 @@ import torch
 from . import _native as nat
 
 
+LAUNCHES = [0]          # kernels of libb200attn launched through this module (graph replays add their node count)
+
+
+def reset_launch_count() -> None:
+    LAUNCHES[0] = 0
+
+
 def _stream() -> int:
+    LAUNCHES[0] += 1        # every wrapper below asks for the stream exactly once per kernel launch
     return torch.cuda.current_stream().cuda_stream
 
 
