@@ -17,6 +17,10 @@
 //   * a kv-head's context that straddles several warps leaves (m, l, O) partials in a small
 //     workspace; the last warp to arrive (per-pair counter) merges them in fixed order, so the
 //     result is deterministic and no second launch is needed.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -25,6 +29,7 @@ constexpr int CHUNK = 16;                          // tokens per pipeline stage
 constexpr int ROW_BYTES = B200_HEAD_DIM * 2;       // one token of one kv head
 constexpr int CHUNK_BYTES = CHUNK * ROW_BYTES;     // 4096
 constexpr int MAX_BATCH = 1024;                    // sequences per launch (prefix table in smem)
+constexpr int MIN_CHUNKS = 8;                      // smallest range handed to one warp (128 tokens)
 
 struct DecodeParams {
     const __nv_bfloat16* q;
@@ -47,7 +52,8 @@ struct DecodeParams {
 
 template <int G, int NWARPS, int NSTAGES>
 struct DecodeSmem {
-    static constexpr int kStageBytes = 2 * CHUNK_BYTES;
+    static constexpr int kQBytes = G * ROW_BYTES;                        // the G query heads of one kv head
+    static constexpr int kStageBytes = 2 * CHUNK_BYTES + kQBytes;       // [K chunk][V chunk][q of the segment]
     static constexpr int kWarpBytes = NSTAGES * kStageBytes;
     static constexpr int kOffStages = 0;
     static constexpr int kOffCum = NWARPS * kWarpBytes;                 // int[MAX_BATCH + 1]
@@ -104,17 +110,10 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     const uint32_t my_bars_u32 = smem_u32(smem + L::kOffBars) + warp * NSTAGES * 8;
     float* pbuf = reinterpret_cast<float*>(smem + L::kOffP) + warp * G * 16;
 
-    // ---- per-warp ring setup: zero the stages (stale rows of a partial chunk must stay finite),
-    //      init the mbarriers -------------------------------------------------------------------
-    {
-        uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* s4 = reinterpret_cast<uint4*>(my_stages);
-        for (int i = lane; i < L::kWarpBytes / 16; i += 32) s4[i] = z;
-        if (lane == 0) {
-            for (int s = 0; s < NSTAGES; ++s) mbar_init(my_bars_u32 + s * 8, 1);
-            mbar_fence_init();
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // ---- per-warp ring setup -----------------------------------------------------------------------
+    if (lane == 0) {
+        for (int s = 0; s < NSTAGES; ++s) mbar_init(my_bars_u32 + s * 8, 1);
+        mbar_fence_init();
     }
 
     // ---- exclusive prefix of per-sequence chunk counts ------------------------------------------
@@ -173,9 +172,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     // ---- this warp's contiguous chunk range -----------------------------------------------------
     const long long C = (long long)hkv * cum[batch];
     const int TW = gridDim.x * NWARPS;
-    const int gw = blockIdx.x * NWARPS + warp;
+    // logical worker id: consecutive workers sit on different SMs, so a small step still spreads over the chip
+    const int gw = warp * gridDim.x + blockIdx.x;
     if (C == 0) return;
-    const long long TWe = C < TW ? C : (long long)TW;     // workers that get at least one chunk
+    // workers that get work: each at least MIN_CHUNKS chunks (a sequence cut into too many segments pays
+    // for it in the merge), never more than there are warps
+    long long TWe = (C + MIN_CHUNKS - 1) / MIN_CHUNKS;
+    TWe = TWe < TW ? TWe : (long long)TW;
     if (gw >= TWe) return;
     const long long c_begin = (long long)gw * C / TWe;
     const long long c_end = (long long)(gw + 1) * C / TWe;
@@ -189,22 +192,32 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     const int j = lane & 15;                              // which 8-wide slice of head_dim
     const int bs_mask = (1 << p.block_shift) - 1;
 
+    // lane 0 keeps the page id of the next chunk to issue one step ahead, so the dependent
+    // block-table load never sits on the issue path
+    int pg_next = 0;
+    if (lane == 0) pg_next = p.block_tables[(int64_t)pi.b * p.bt_stride + ((pi.ck * CHUNK) >> p.block_shift)];
+
     auto issue = [&](int i) {                             // chunk i of this warp's range
         if (lane == 0) {
             const int slot = i % NSTAGES;
             const int tok0 = pi.ck * CHUNK;
-            const int page = p.block_tables[(int64_t)pi.b * p.bt_stride + (tok0 >> p.block_shift)];
+            const int page = pg_next;
             int valid = pi.ctx - tok0;
             valid = valid > CHUNK ? CHUNK : valid;
             const uint32_t bytes = (uint32_t)valid * ROW_BYTES;
             const int64_t row = (((int64_t)page * hkv + pi.h) << p.block_shift) + (tok0 & bs_mask);
             const uint32_t bar = my_bars_u32 + slot * 8;
             const uint32_t dst = my_stages_u32 + slot * L::kStageBytes;
-            mbar_expect_tx(bar, 2 * bytes);
+            const bool seg_first = (pi.ck == 0) || (i == 0);      // the consumer starts a segment on this chunk
+            mbar_expect_tx(bar, 2 * bytes + (seg_first ? (uint32_t)L::kQBytes : 0u));
             bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
             bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
+            if (seg_first)
+                bulk_g2s(dst + 2 * CHUNK_BYTES, p.q + (int64_t)pi.b * p.q_stride + pi.h * G * B200_HEAD_DIM, L::kQBytes, bar);
         }
         pi.advance(cum, ctxs, batch, hkv);
+        if (lane == 0 && i + 1 < n_local)
+            pg_next = p.block_tables[(int64_t)pi.b * p.bt_stride + ((pi.ck * CHUNK) >> p.block_shift)];
     };
 
     __syncwarp();
@@ -220,12 +233,16 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     for (int i = 0; i < n_local; ++i) {
         if (i + NSTAGES - 1 < n_local) issue(i + NSTAGES - 1);
 
-        if (seg_start) {
+        const int slot = i % NSTAGES;
+        mbar_wait(my_bars_u32 + slot * 8, (i / NSTAGES) & 1);
+        const uint8_t* ks = my_stages + slot * L::kStageBytes;
+        const uint8_t* vs = ks + CHUNK_BYTES;
+
+        if (seg_start) {                                  // q arrived with this chunk
             seg_start = false;
 #pragma unroll
             for (int g = 0; g < G; ++g) {
-                const uint4 w = *reinterpret_cast<const uint4*>(
-                    p.q + (int64_t)ci.b * p.q_stride + (ci.h * G + g) * B200_HEAD_DIM + j * 8);
+                const uint4 w = *reinterpret_cast<const uint4*>(ks + 2 * CHUNK_BYTES + g * ROW_BYTES + j * 16);
                 unpack8(w, qf[g]);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { qf[g][e] *= p.scale_log2; o[g][e] = 0.f; }
@@ -233,11 +250,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
                 l[g] = 0.f;
             }
         }
-
-        const int slot = i % NSTAGES;
-        mbar_wait(my_bars_u32 + slot * 8, (i / NSTAGES) & 1);
-        const uint8_t* ks = my_stages + slot * L::kStageBytes;
-        const uint8_t* vs = ks + CHUNK_BYTES;
 
         // ---- S = q K^T : half-warp per token, 16 lanes x 8 dims ---------------------------------
         float acc[G][8];
@@ -307,17 +319,26 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
             pr[g][0] = a.x; pr[g][1] = a.y; pr[g][2] = a.z; pr[g][3] = a.w;
             pr[g][4] = c4.x; pr[g][5] = c4.y; pr[g][6] = c4.z; pr[g][7] = c4.w;
         }
+        // Rows beyond the context in the last chunk of a sequence were not copied: the stage still holds
+        // whatever an earlier chunk left there (or uninitialised shared memory); their p is 0 but 0 * NaN
+        // is NaN, so that chunk takes a path that zeroes them.
+        auto pv = [&](auto partial) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const uint4 w = *reinterpret_cast<const uint4*>(vs + (2 * it + hw) * ROW_BYTES + j * 16);
-            float vf[8];
-            unpack8(w, vf);
+            for (int it = 0; it < 8; ++it) {
+                uint4 w = *reinterpret_cast<const uint4*>(vs + (2 * it + hw) * ROW_BYTES + j * 16);
+                if constexpr (decltype(partial)::value) {
+                    if (2 * it + hw >= nvalid) w = make_uint4(0, 0, 0, 0);
+                }
+                float vf[8];
+                unpack8(w, vf);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
+                for (int g = 0; g < G; ++g) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pr[g][it], vf[e], o[g][e]);
+                    for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pr[g][it], vf[e], o[g][e]);
+                }
             }
-        }
+        };
+        if (nvalid == CHUNK) pv(std::false_type{}); else pv(std::true_type{});
         __syncwarp();   // every lane is done with this stage and with pbuf
 
         // ---- end of a segment (kv head exhausted, or this warp's range ends) ---------------------
@@ -370,37 +391,49 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
                 int old = 0;
                 if (lane == 0) old = atomicAdd(p.counters + pair, 1);
                 old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == nseg - 1) {               // last segment in: merge in fixed order
+                if (old == nseg - 1) {               // last segment in: merge, in an order fixed by the data
                     __threadfence();
-                    if (hw == 0) {
+                    // half-warp hw folds segments k = hw, hw+2, ... with a running maximum, then the halves meet
+                    float M[G], Ls[G], r[G][8];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        M[g] = -INFINITY; Ls[g] = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) r[g][e] = 0.f;
+                    }
+#pragma unroll 2
+                    for (int k = hw; k < nseg; k += 2) {
+                        const int sl = k == 0 ? TW + pair : w_first + k;
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
-                            float M = -INFINITY;
-                            for (int k = 0; k < nseg; ++k) {
-                                const int sl = k == 0 ? TW + pair : w_first + k;
-                                M = fmaxf(M, __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2));
-                            }
-                            float Ls = 0.f;
-                            float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            for (int k = 0; k < nseg; ++k) {
-                                const int sl = k == 0 ? TW + pair : w_first + k;
-                                const float mk = __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2);
-                                const float lk = __ldcg(p.part_ml + ((int64_t)sl * G + g) * 2 + 1);
-                                const float wgt = fast_exp2(mk - M);
-                                Ls = fmaf(lk, wgt, Ls);
-                                const float4* s4 = reinterpret_cast<const float4*>(
-                                    p.part_o + ((int64_t)sl * G + g) * B200_HEAD_DIM + j * 8);
-                                const float4 a = __ldcg(s4), c4 = __ldcg(s4 + 1);
-                                r[0] = fmaf(a.x, wgt, r[0]); r[1] = fmaf(a.y, wgt, r[1]);
-                                r[2] = fmaf(a.z, wgt, r[2]); r[3] = fmaf(a.w, wgt, r[3]);
-                                r[4] = fmaf(c4.x, wgt, r[4]); r[5] = fmaf(c4.y, wgt, r[5]);
-                                r[6] = fmaf(c4.z, wgt, r[6]); r[7] = fmaf(c4.w, wgt, r[7]);
-                            }
-                            const float inv = 1.f / Ls;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) r[e] *= inv;
-                            *reinterpret_cast<uint4*>(orow + g * B200_HEAD_DIM) = pack8(r);
+                            const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml + ((int64_t)sl * G + g) * 2));
+                            const float4* s4 = reinterpret_cast<const float4*>(
+                                p.part_o + ((int64_t)sl * G + g) * B200_HEAD_DIM + j * 8);
+                            const float4 a = __ldcg(s4), c4 = __ldcg(s4 + 1);
+                            const float Mn = fmaxf(M[g], ml.x);
+                            const float so = fast_exp2(M[g] - Mn), sn = fast_exp2(ml.x - Mn);
+                            M[g] = Mn;
+                            Ls[g] = Ls[g] * so + ml.y * sn;
+                            r[g][0] = r[g][0] * so + a.x * sn; r[g][1] = r[g][1] * so + a.y * sn;
+                            r[g][2] = r[g][2] * so + a.z * sn; r[g][3] = r[g][3] * so + a.w * sn;
+                            r[g][4] = r[g][4] * so + c4.x * sn; r[g][5] = r[g][5] * so + c4.y * sn;
+                            r[g][6] = r[g][6] * so + c4.z * sn; r[g][7] = r[g][7] * so + c4.w * sn;
                         }
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float Mo = __shfl_xor_sync(0xffffffffu, M[g], 16);
+                        const float Lo = __shfl_xor_sync(0xffffffffu, Ls[g], 16);
+                        const float Mn = fmaxf(M[g], Mo);                       // nseg >= 2: both halves saw a segment
+                        const float sa = fast_exp2(M[g] - Mn), sb = fast_exp2(Mo - Mn);
+                        const float inv = 1.f / (Ls[g] * sa + Lo * sb);
+                        float res[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float ro = __shfl_xor_sync(0xffffffffu, r[g][e], 16);
+                            res[e] = (r[g][e] * sa + ro * sb) * inv;
+                        }
+                        if (hw == 0) *reinterpret_cast<uint4*>(orow + g * B200_HEAD_DIM) = pack8(res);
                     }
                     if (lane == 0) p.counters[pair] = 0;   // leave the workspace clean for the next launch
                 }
@@ -411,20 +444,58 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     }
 }
 
-constexpr int kWarps = 8;
-constexpr int kStages = 3;
+constexpr int kMaxWarps = 16;   // workspace is sized for the widest variant
+
+// (warps per CTA, ring depth) variants; B200_DECODE_CFG=<warps>x<stages> picks one at first use (tuning knob).
+template <int G, int NW, int NS>
+int launch_variant(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
+    using L = DecodeSmem<G, NW, NS>;
+    if constexpr (L::kTotal > 227 * 1024) {
+        return B200_EUNSUPPORTED;
+    } else {
+        auto kern = paged_decode_kernel<G, NW, NS>;
+        static bool configured = false;
+        if (!configured) {
+            B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+            configured = true;
+        }
+        kern<<<ctx->sm_count, NW * 32, L::kTotal, stream>>>(prm);
+        return b200_launch_status(ctx);
+    }
+}
+
+int decode_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200_DECODE_CFG");
+        v = 0;
+        if (e && !strcmp(e, "12x2")) v = 1;
+        if (e && !strcmp(e, "10x2")) v = 2;
+        if (e && !strcmp(e, "8x3")) v = 3;
+        if (e && !strcmp(e, "6x2")) v = 4;
+        if (e && !strcmp(e, "4x2")) v = 5;
+        if (e && !strcmp(e, "6x3")) v = 6;
+        if (e && !strcmp(e, "4x3")) v = 7;
+    }
+    return v;
+}
 
 template <int G>
 int launch_decode(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
-    using L = DecodeSmem<G, kWarps, kStages>;
-    auto kern = paged_decode_kernel<G, kWarps, kStages>;
-    static bool configured = false;
-    if (!configured) {
-        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
+    if constexpr (G == 8) {
+        return launch_variant<G, 8, 2>(ctx, prm, stream);     // 3 stages of 10 KB x 8 warps exceed 227 KB
+    } else {
+        switch (decode_variant()) {
+            case 1: return launch_variant<G, 12, 2>(ctx, prm, stream);
+            case 2: return launch_variant<G, 10, 2>(ctx, prm, stream);
+            case 3: return launch_variant<G, 8, 3>(ctx, prm, stream);
+            case 4: return launch_variant<G, 6, 2>(ctx, prm, stream);
+            case 5: return launch_variant<G, 4, 2>(ctx, prm, stream);
+            case 6: return launch_variant<G, 6, 3>(ctx, prm, stream);
+            case 7: return launch_variant<G, 4, 3>(ctx, prm, stream);
+            default: return launch_variant<G, 8, 2>(ctx, prm, stream);
+        }
     }
-    kern<<<ctx->sm_count, kWarps * 32, L::kTotal, stream>>>(prm);
-    return b200_launch_status(ctx);
 }
 
 }  // namespace
@@ -436,7 +507,7 @@ struct WsLayout {
 //  launches][part_ml][part_o]; the two scratch regions may move with the batch size.
 static WsLayout ws_layout(int sm_count, int batch, int hkv, int G) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t slots = (size_t)sm_count * kWarps + (size_t)batch * hkv;
+    const size_t slots = (size_t)sm_count * kMaxWarps + (size_t)batch * hkv;
     WsLayout w;
     size_t off = al((size_t)MAX_BATCH * hkv * sizeof(int));
     w.off_ml = off;
