@@ -1,0 +1,22 @@
+"""Tensor parallelism over NCCL (needs >= 2 GPUs on the box; skipped otherwise)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("eager", ["1", "0"])
+def test_tp2_engine_matches_oracle(eager):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ, TP_EAGER=eager)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29555 + int(eager)), os.path.join(ROOT, "tests", "tp_worker.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "TP_RESULT" in r.stdout and '"ok": true' in r.stdout
