@@ -145,21 +145,65 @@ class LLMEngine:
         for prompt, sp in zip(prompts, sampling_params):
             self._add_request(prompt, sp)
         done: dict[int, list[int]] = {}
-        prefill_tps = decode_tps = 0.0
-        while not self.is_finished():
-            t0 = perf_counter()
-            finished, num_tokens = self._step()
-            dt = perf_counter() - t0
+        stats = {"prefill": 0.0, "decode": 0.0}
+
+        def on_step(finished, num_tokens, dt):
             if num_tokens > 0:
-                prefill_tps = num_tokens / dt
+                stats["prefill"] = num_tokens / dt
             else:
-                decode_tps = -num_tokens / dt
-            for seq_id, toks in finished:
-                done[seq_id] = toks
+                stats["decode"] = -num_tokens / dt
+            for seq in finished:
+                done[seq.seq_id] = seq.completion_token_ids
             if pbar is not None:
-                pbar.set_postfix({"Prefill": f"{int(prefill_tps)}tok/s", "Decode": f"{int(decode_tps)}tok/s"})
+                pbar.set_postfix({"Prefill": f"{int(stats['prefill'])}tok/s", "Decode": f"{int(stats['decode'])}tok/s"})
                 pbar.update(len(finished))
+
+        self._run_overlapped(on_step)
         if pbar is not None:
             pbar.close()
         ordered = [done[k] for k in sorted(done)]
         return [{"text": self.tokenizer.decode(t), "token_ids": t} for t in ordered]
+
+    def _run_overlapped(self, on_step) -> None:
+        """The reference's step loop (llm_engine.py:49-55, 73-86) with the host work of step N+1 done while the
+        GPU runs step N.
+
+        What the next schedule needs from a finished step is (a) which sequences ended and (b) the sampled
+        token values.  (a) depends on the values only through EOS, so when no sequence of the batch can stop on
+        EOS (ignore_eos) the whole postprocess -> schedule -> metadata staging of the next step is computed
+        first with a placeholder token, and the values are patched in when they arrive: the bookkeeping is
+        exactly the synchronous one, only earlier.  A batch that can hit EOS takes the synchronous order."""
+        sched, runner = self.scheduler, self.model_runner
+        PENDING = -1
+        if sched.is_finished():
+            return
+        seqs, is_prefill = sched.schedule()
+        runner.call("launch", seqs, is_prefill)
+        t0 = perf_counter()
+        while True:
+            num_tokens = sum(s.num_scheduled_tokens for s in seqs) if is_prefill else -len(seqs)
+            nxt, staged = None, None
+            if all(s.ignore_eos for s in seqs):
+                before = [s.num_tokens for s in seqs]
+                sched.postprocess(seqs, [PENDING] * len(seqs), is_prefill)
+                if not sched.is_finished():
+                    nxt = sched.schedule()
+                    if not nxt[1]:
+                        staged = runner.stage_decode(nxt[0])
+                tokens = runner.call("collect")
+                for s, b, t in zip(seqs, before, tokens):
+                    if s.num_tokens != b:                       # a token was appended: give it its value
+                        s.token_ids[-1] = t
+                        s.last_token = t
+            else:
+                tokens = runner.call("collect")
+                sched.postprocess(seqs, tokens, is_prefill)
+                if not sched.is_finished():
+                    nxt = sched.schedule()
+            now = perf_counter()
+            on_step([s for s in seqs if s.is_finished], num_tokens, max(now - t0, 1e-9))
+            t0 = now
+            if nxt is None:
+                return
+            seqs, is_prefill = nxt
+            runner.launch(seqs, is_prefill, staged)

@@ -39,21 +39,26 @@ def _align(n: int) -> int:
 
 
 class _Staging:
-    """A pinned host byte buffer mirrored by a device byte buffer; regions are typed views."""
+    """Pinned host byte buffers (ping-pong) mirrored by one device byte buffer; regions are typed views."""
 
-    def __init__(self, nbytes: int):
-        self.host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    def __init__(self, nbytes: int, hosts: int = 1):
+        self.hosts = [torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(hosts)]
         self.dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        self.host_np = self.host.numpy()
+        self.host_nps = [h.numpy() for h in self.hosts]
 
-    def views(self, off: int, count: int, np_dtype, torch_dtype):
+    def host_view(self, off: int, count: int, np_dtype, which: int = 0):
         nbytes = count * np.dtype(np_dtype).itemsize
-        h = self.host_np[off:off + nbytes].view(np_dtype)
-        d = self.dev[off:off + nbytes].view(torch_dtype)
-        return h, d
+        return self.host_nps[which][off:off + nbytes].view(np_dtype)
 
-    def upload(self, nbytes: int):
-        self.dev[:nbytes].copy_(self.host[:nbytes], non_blocking=True)
+    def dev_view(self, off: int, count: int, np_dtype, torch_dtype):
+        nbytes = count * np.dtype(np_dtype).itemsize
+        return self.dev[off:off + nbytes].view(torch_dtype)
+
+    def views(self, off: int, count: int, np_dtype, torch_dtype, which: int = 0):
+        return self.host_view(off, count, np_dtype, which), self.dev_view(off, count, np_dtype, torch_dtype)
+
+    def upload(self, nbytes: int, which: int = 0):
+        self.dev[:nbytes].copy_(self.hosts[which][:nbytes], non_blocking=True)
 
 
 class ModelRunner:
@@ -142,25 +147,29 @@ class ModelRunner:
             o = _align(o + count * size)
         self.d_bytes = o
         prefill_bytes = _align(8) + 2 * _align(T * 8) + _align(T * 4) + 2 * _align((S + 1) * 4) + _align(S * 4) + _align(S * W * 4)
-        self.stage = _Staging(self.d_bytes)
+        self.stage = _Staging(self.d_bytes, hosts=2)         # ping-pong: step N+1 is staged while step N runs
         self.pstage = _Staging(prefill_bytes)
         st = self.stage
-        self.h_step, self.g_step = st.views(self.d_off["step"], 1, np.int64, torch.int64)
-        self.h_ids, self.g_ids = st.views(self.d_off["ids"], mb, np.int64, torch.int64)
-        self.h_pos, self.g_pos = st.views(self.d_off["pos"], mb, np.int64, torch.int64)
-        self.h_slot, self.g_slot = st.views(self.d_off["slot"], mb, np.int32, torch.int32)
-        self.h_ctx, self.g_ctx = st.views(self.d_off["ctx"], mb, np.int32, torch.int32)
-        self.h_temp, self.g_temp = st.views(self.d_off["temp"], mb, np.float32, torch.float32)
-        h_bt, g_bt = st.views(self.d_off["bt"], mb * W, np.int32, torch.int32)
-        self.h_bt, self.g_bt = h_bt.reshape(mb, W), g_bt.view(mb, W)
-        self.h_bt[:] = 0
+        spec = (("step", 1, np.int64, torch.int64), ("ids", mb, np.int64, torch.int64), ("pos", mb, np.int64, torch.int64),
+                ("slot", mb, np.int32, torch.int32), ("ctx", mb, np.int32, torch.int32), ("temp", mb, np.float32, torch.float32),
+                ("bt", mb * W, np.int32, torch.int32))
+        self.hd = [{name: st.host_view(self.d_off[name], cnt, npdt, k) for name, cnt, npdt, _ in spec} for k in range(2)]
+        for h in self.hd:
+            h["bt"] = h["bt"].reshape(mb, W)
+            h["bt"][:] = 0
+        g = {name: st.dev_view(self.d_off[name], cnt, npdt, tdt) for name, cnt, npdt, tdt in spec}
+        self.g_step, self.g_ids, self.g_pos, self.g_slot = g["step"], g["ids"], g["pos"], g["slot"]
+        self.g_ctx, self.g_temp, self.g_bt = g["ctx"], g["temp"], g["bt"].view(mb, W)
         self.g_bt.zero_()
+        self._host_k = 0
         self.g_tokens = torch.zeros(S, dtype=torch.int64, device="cuda")
         self.g_keys = torch.zeros(S, dtype=torch.int64, device="cuda")
         self.h_tokens = torch.empty(S, dtype=torch.int64, pin_memory=True)
         self.h_tokens_np = self.h_tokens.numpy()
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = 0
+        self._done = torch.cuda.Event()
+        self._inflight = 0
 
     # ---- init-time passes -----------------------------------------------------------------------
     def warmup_model(self):
@@ -288,27 +297,46 @@ class ModelRunner:
                     slot, None, bt)
         return views["input_ids"], views["positions"], views["temps"], views["step"]
 
-    def prepare_decode(self, seqs: list[Sequence], padded: int):
-        """Fill the static decode buffers for len(seqs) live rows padded to `padded` rows and upload them."""
+    def _padded_rows(self, n: int) -> int:
+        use_graph = (not self.enforce_eager) and n <= self.max_bs and bool(self.graphs)
+        return next(b for b in self.graph_bs if b >= n) if use_graph else n
+
+    def stage_decode(self, seqs: list[Sequence]) -> int:
+        """Fill the next pinned decode buffer for this batch (graph-padded) WITHOUT touching the GPU; returns the
+        buffer index.  input_ids / step are refreshed at launch, so this may run while the previous step is still
+        executing and its sampled tokens are not known yet."""
+        self._host_k ^= 1
+        k = self._host_k
+        h = self.hd[k]
         a = self.decode_arrays(seqs)
         n = len(seqs)
-        self.h_step[0] = self.sample_step
-        self.h_ids[:n] = a["input_ids"]
-        self.h_pos[:n] = a["positions"]
-        self.h_slot[:n] = a["slot_mapping"]
-        self.h_ctx[:n] = a["context_lens"]
-        self.h_temp[:n] = np.fromiter((s.temperature for s in seqs), dtype=np.float32, count=n)
+        padded = self._padded_rows(n)
+        h["ids"][:n] = a["input_ids"]
+        h["pos"][:n] = a["positions"]
+        h["slot"][:n] = a["slot_mapping"]
+        h["ctx"][:n] = a["context_lens"]
+        h["temp"][:n] = np.fromiter((s.temperature for s in seqs), dtype=np.float32, count=n)
         if padded > n:                                       # graph padding rows (model_runner.py:206-208)
-            self.h_ids[n:padded] = 0
-            self.h_pos[n:padded] = 0
-            self.h_slot[n:padded] = -1
-            self.h_ctx[n:padded] = 0
-            self.h_temp[n:padded] = 0
+            h["ids"][n:padded] = 0
+            h["pos"][n:padded] = 0
+            h["slot"][n:padded] = -1
+            h["ctx"][n:padded] = 0
+            h["temp"][n:padded] = 0
         bt = a["block_tables"]
-        self.h_bt[:n, :bt.shape[1]] = bt
-        W = self.max_blocks
-        nbytes = self.d_off["bt"] + padded * W * 4
-        self.stage.upload(nbytes)
+        h["bt"][:n, :bt.shape[1]] = bt
+        return k
+
+    def prepare_decode(self, seqs: list[Sequence], padded: int, staged: int | None = None):
+        """Upload a staged decode buffer (staging it now unless `staged` names one) and set the Context."""
+        n = len(seqs)
+        if staged is None:
+            k = self.stage_decode(seqs)
+        else:                                                # staged early: only the token ids were unknown then
+            k = staged
+            self.hd[k]["ids"][:n] = np.fromiter((s.last_token for s in seqs), dtype=np.int64, count=n)
+        self.hd[k]["step"][0] = self.sample_step
+        nbytes = self.d_off["bt"] + padded * self.max_blocks * 4
+        self.stage.upload(nbytes, k)
         self.h2d_bytes_last = nbytes
         set_context(False, slot_mapping=self.g_slot[:padded], context_lens=self.g_ctx[:padded],
                     block_tables=self.g_bt[:padded])
@@ -327,11 +355,17 @@ class ModelRunner:
             dist.all_reduce(keys, op=dist.ReduceOp.MAX)
             self.g_tokens[:rows].copy_(ops.tokens_from_keys(keys))
 
-    @torch.inference_mode()
     def run(self, seqs: list[Sequence], is_prefill: bool) -> list[int]:
+        self.launch(seqs, is_prefill)
+        return self.collect()
+
+    @torch.inference_mode()
+    def launch(self, seqs: list[Sequence], is_prefill: bool, staged: int | None = None) -> None:
+        """Enqueue one step (metadata upload, forward, sampling, token read-back) without waiting for it."""
         n = len(seqs)
         self.sample_step += 1
         prof = self._prof
+        ev0 = None
         if is_prefill:
             ids, pos, temps, step_dev = self.prepare_prefill(seqs)
             if prof is not None:
@@ -339,15 +373,14 @@ class ModelRunner:
                 ev0.record()
             self._forward_and_sample(ids, pos, temps, step_dev, n)
         else:
-            use_graph = (not self.enforce_eager) and n <= self.max_bs and bool(self.graphs)
-            padded = next(b for b in self.graph_bs if b >= n) if use_graph else n
             if n > self.cap_bs:
                 raise RuntimeError(f"decode batch {n} exceeds max_num_seqs = {self.cap_bs}")
-            self.prepare_decode(seqs, padded)
+            padded = self._padded_rows(n)
+            self.prepare_decode(seqs, padded, staged)
             if prof is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            if use_graph:
+            if padded in self.graphs and not self.enforce_eager and n <= self.max_bs:
                 self.graphs[padded].replay()
                 ops.LAUNCHES[0] += self.graph_kernels[padded]
             else:
@@ -355,16 +388,20 @@ class ModelRunner:
         if prof is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
-        self.h_tokens[:n].copy_(self.g_tokens[:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()            # the step's only host sync
-        self.d2h_bytes_last = n * 8
-        if prof is not None:
             prof["events"].append((ev0, ev1))
             prof["h2d"] += self.h2d_bytes_last
-            prof["d2h"] += self.d2h_bytes_last
+            prof["d2h"] += n * 8
             prof["steps"] += 1
+        self.h_tokens[:n].copy_(self.g_tokens[:n], non_blocking=True)
+        self._done.record()
+        self._inflight = n
+        self.d2h_bytes_last = n * 8
+
+    def collect(self) -> list[int]:
+        """Wait for the step enqueued by launch() (the step's only host sync) and return its token ids."""
+        self._done.synchronize()
         reset_context()
-        return self.h_tokens_np[:n].tolist()
+        return self.h_tokens_np[:self._inflight].tolist()
 
     @torch.inference_mode()
     def capture_cudagraph(self):
@@ -374,12 +411,14 @@ class ModelRunner:
         self.graph_bs = [b for b in (1, 2, 4, 8) if b <= max_bs] + list(range(16, max_bs + 1, 16))
         if max_bs not in self.graph_bs:
             self.graph_bs.append(max_bs)
-        self.h_ctx[:] = 0
-        self.h_slot[:] = -1
-        self.h_ids[:] = 0
-        self.h_pos[:] = 0
-        self.h_temp[:] = 0
-        self.stage.upload(self.d_bytes)
+        h = self.hd[0]
+        h["ctx"][:] = 0
+        h["slot"][:] = -1
+        h["ids"][:] = 0
+        h["pos"][:] = 0
+        h["temp"][:] = 0
+        h["step"][0] = 0
+        self.stage.upload(self.d_bytes, 0)
         torch.cuda.synchronize()
         for bs in reversed(self.graph_bs):
             set_context(False, slot_mapping=self.g_slot[:bs], context_lens=self.g_ctx[:bs], block_tables=self.g_bt[:bs])
