@@ -200,6 +200,43 @@ def test_prefill_paged_prefix_and_chunk(ops, bs):
     assert_close_bf16(got, want, f"paged prefill bs={bs}")
 
 
+def test_prefill_long_causal_and_rescale(ops):
+    """Many key blocks per query tile, and scores whose running maximum keeps growing by far more than 2^8, so the
+    in-TMEM accumulator is rescaled repeatedly (the lazy-rescale path of the tcgen05 kernel)."""
+    hq, hkv = 4, 2
+    lens = [1500, 900, 257]
+    tot = sum(lens)
+    g = torch.Generator().manual_seed(77)
+    q = (torch.randn(tot, hq, 128, generator=g) * 3.0).to(torch.bfloat16)
+    k = torch.randn(tot, hkv, 128, generator=g)
+    ramp = torch.cat([torch.linspace(0.2, 4.0, n) for n in lens]).view(tot, 1, 1)     # later keys score much higher
+    k = (k * ramp).to(torch.bfloat16)
+    v = torch.randn(tot, hkv, 128, generator=g).to(torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    scale = 128 ** -0.5
+    want = varlen_prefill_ref(q, k, v, cu, cu, scale, p_dtype=torch.bfloat16)
+    got = ops.paged_prefill(0, q.cuda(), k.cuda(), v.cuda(), cu.cuda(), cu.cuda(), max(lens), max(lens), scale)
+    assert_close_bf16(got, want, "long causal prefill with growing maxima", ulps=3.0, rel_l2=6e-3)
+
+
+@pytest.mark.parametrize("bs", [32, 64, 128])
+def test_prefill_paged_block_sizes(ops, bs):
+    hq, hkv = 16, 2                                       # G = 8
+    len_k = [700, 129, 64]
+    len_q = [300, 129, 1]
+    nblk = sum((c + bs - 1) // bs for c in len_k) + 1
+    kv, ks, vs = bind_random_cache(ops, 1, nblk, hkv, bs, seed=61)
+    tables = make_tables(len_k, bs, nblk, seed=9)
+    q = bf(sum(len_q), hq, 128, seed=16)
+    cu_q = torch.tensor([0] + list(torch.tensor(len_q).cumsum(0)), dtype=torch.int32)
+    cu_k = torch.tensor([0] + list(torch.tensor(len_k).cumsum(0)), dtype=torch.int32)
+    scale = 128 ** -0.5
+    want = varlen_prefill_ref(q, None, None, cu_q, cu_k, scale, tables, ks[0], vs[0], p_dtype=torch.bfloat16)
+    got = ops.paged_prefill(0, q.cuda(), None, None, cu_q.cuda(), cu_k.cuda(), max(len_q), max(len_k), scale,
+                            block_tables=tables.cuda(), num_kv_heads=hkv)
+    assert_close_bf16(got, want, f"paged prefill bs={bs} G=8")
+
+
 # ---------------------------------------------------------------------------------------------
 # K5-K8 fused elementwise ops
 # ---------------------------------------------------------------------------------------------
