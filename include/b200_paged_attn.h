@@ -139,6 +139,12 @@ int b200_silu_mul(const void* x, void* out, int rows, int inter, void* stream);
 int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden,
                    void* stream);
 
+/* Feeds a decode step's input_ids straight from the previous step's sampled tokens, on the device:
+ *   ids[i] = prev_tokens[src[i]]  where src[i] >= 0,  unchanged otherwise.
+ * Replaces the host round trip of ModelRunner.prepare_decode (engine/model_runner.py:177, seq.last_token of a
+ * token that was sampled one step earlier), so step N+1 can be enqueued before step N's tokens reach the host. */
+int b200_gather_tokens(int64_t* ids, const int32_t* src, const int64_t* prev_tokens, int n, void* stream);
+
 /* Sampler.forward (layers/sampler.py:7-12) plus the greedy branch the north-star adds:
  *   temperature[r] == 0 : out[r] = argmax_j logits[r, j]  (lowest index on ties)
  *   temperature[r]  > 0 : exponential race  argmax_j softmax(logits/t)_j / E_j,  E_j ~ Exp(1)

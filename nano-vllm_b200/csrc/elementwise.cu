@@ -181,6 +181,14 @@ __global__ void __launch_bounds__(128) embedding_kernel(const int64_t* __restric
     for (int i = threadIdx.x; i < hidden_vec; i += 128) dst[i] = src[i];
 }
 
+__global__ void gather_tokens_kernel(int64_t* ids, const int32_t* __restrict__ src, const int64_t* __restrict__ prev, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int s = src[i];
+        if (s >= 0) ids[i] = prev[s];
+    }
+}
+
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -268,5 +276,12 @@ extern "C" int b200_embedding(const int64_t* ids, const void* table, void* out, 
     if (n == 0) return B200_OK;
     embedding_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, static_cast<const __nv_bfloat16*>(table), static_cast<__nv_bfloat16*>(out), hidden / 8);
+    return b200_launch_status(nullptr);
+}
+
+extern "C" int b200_gather_tokens(int64_t* ids, const int32_t* src, const int64_t* prev_tokens, int n, void* stream) {
+    if (!ids || !src || !prev_tokens || n < 0) return B200_EINVAL;
+    if (n == 0) return B200_OK;
+    gather_tokens_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, src, prev_tokens, n);
     return b200_launch_status(nullptr);
 }

@@ -171,8 +171,10 @@ class LLMEngine:
         What the next schedule needs from a finished step is (a) which sequences ended and (b) the sampled
         token values.  (a) depends on the values only through EOS, so when no sequence of the batch can stop on
         EOS (ignore_eos) the whole postprocess -> schedule -> metadata staging of the next step is computed
-        first with a placeholder token, and the values are patched in when they arrive: the bookkeeping is
-        exactly the synchronous one, only earlier.  A batch that can hit EOS takes the synchronous order."""
+        first with a placeholder token, a following decode step is even enqueued on the GPU (its input ids are
+        gathered on the device from the running step's output), and the values are patched into the host state
+        when they arrive: the bookkeeping is exactly the synchronous one, only earlier.  A batch that can hit EOS
+        takes the synchronous order."""
         sched, runner = self.scheduler, self.model_runner
         PENDING = -1
         if sched.is_finished():
@@ -182,14 +184,19 @@ class LLMEngine:
         t0 = perf_counter()
         while True:
             num_tokens = sum(s.num_scheduled_tokens for s in seqs) if is_prefill else -len(seqs)
-            nxt, staged = None, None
+            nxt, launched = None, False
             if all(s.ignore_eos for s in seqs):
                 before = [s.num_tokens for s in seqs]
                 sched.postprocess(seqs, [PENDING] * len(seqs), is_prefill)
                 if not sched.is_finished():
                     nxt = sched.schedule()
                     if not nxt[1]:
-                        staged = runner.stage_decode(nxt[0])
+                        # a decode step: its metadata needs no token value and its input ids are gathered on the
+                        # device from the step still running, so enqueue it now -- the GPU never waits for the host
+                        row_of = {id(s): i for i, (s, b) in enumerate(zip(seqs, before)) if s.num_tokens != b}
+                        src = [row_of.get(id(s), -1) for s in nxt[0]]
+                        runner.launch(nxt[0], False, runner.stage_decode(nxt[0]), src)
+                        launched = True
                 tokens = runner.call("collect")
                 for s, b, t in zip(seqs, before, tokens):
                     if s.num_tokens != b:                       # a token was appended: give it its value
@@ -206,4 +213,5 @@ class LLMEngine:
             if nxt is None:
                 return
             seqs, is_prefill = nxt
-            runner.launch(seqs, is_prefill, staged)
+            if not launched:
+                runner.launch(seqs, is_prefill)

@@ -18,6 +18,7 @@ B200-first differences (DESIGN.md "runner"):
 from __future__ import annotations
 
 import os
+from collections import deque
 
 import numpy as np
 import torch
@@ -142,7 +143,7 @@ class ModelRunner:
         self.d_off = {}
         mb = self.cap_bs
         for name, count, size in (("step", 1, 8), ("ids", mb, 8), ("pos", mb, 8), ("slot", mb, 4), ("ctx", mb, 4),
-                                  ("temp", mb, 4), ("bt", mb * W, 4)):
+                                  ("temp", mb, 4), ("src", mb, 4), ("bt", mb * W, 4)):
             self.d_off[name] = o
             o = _align(o + count * size)
         self.d_bytes = o
@@ -152,24 +153,25 @@ class ModelRunner:
         st = self.stage
         spec = (("step", 1, np.int64, torch.int64), ("ids", mb, np.int64, torch.int64), ("pos", mb, np.int64, torch.int64),
                 ("slot", mb, np.int32, torch.int32), ("ctx", mb, np.int32, torch.int32), ("temp", mb, np.float32, torch.float32),
-                ("bt", mb * W, np.int32, torch.int32))
+                ("src", mb, np.int32, torch.int32), ("bt", mb * W, np.int32, torch.int32))
         self.hd = [{name: st.host_view(self.d_off[name], cnt, npdt, k) for name, cnt, npdt, _ in spec} for k in range(2)]
         for h in self.hd:
             h["bt"] = h["bt"].reshape(mb, W)
             h["bt"][:] = 0
         g = {name: st.dev_view(self.d_off[name], cnt, npdt, tdt) for name, cnt, npdt, tdt in spec}
         self.g_step, self.g_ids, self.g_pos, self.g_slot = g["step"], g["ids"], g["pos"], g["slot"]
-        self.g_ctx, self.g_temp, self.g_bt = g["ctx"], g["temp"], g["bt"].view(mb, W)
+        self.g_ctx, self.g_temp, self.g_bt, self.g_src = g["ctx"], g["temp"], g["bt"].view(mb, W), g["src"]
         self.g_bt.zero_()
         self._host_k = 0
         self.g_tokens = torch.zeros(S, dtype=torch.int64, device="cuda")
         self.g_keys = torch.zeros(S, dtype=torch.int64, device="cuda")
-        self.h_tokens = torch.empty(S, dtype=torch.int64, pin_memory=True)
-        self.h_tokens_np = self.h_tokens.numpy()
+        self.h_tokens = [torch.empty(S, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        self.h_tokens_np = [t.numpy() for t in self.h_tokens]
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = 0
-        self._done = torch.cuda.Event()
-        self._inflight = 0
+        self._done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._launches = 0
+        self._pending: deque = deque()            # (read-back buffer, rows) of steps launched but not collected
 
     # ---- init-time passes -----------------------------------------------------------------------
     def warmup_model(self):
@@ -326,8 +328,12 @@ class ModelRunner:
         h["bt"][:n, :bt.shape[1]] = bt
         return k
 
-    def prepare_decode(self, seqs: list[Sequence], padded: int, staged: int | None = None):
-        """Upload a staged decode buffer (staging it now unless `staged` names one) and set the Context."""
+    def prepare_decode(self, seqs: list[Sequence], padded: int, staged: int | None = None, src=None):
+        """Upload a staged decode buffer (staging it now unless `staged` names one) and set the Context.
+
+        `src` (optional, one int per row): row of the PREVIOUS step's sampled tokens that is this row's input id, or
+        -1 when the id is already known on the host.  With it the step can be enqueued before the previous step's
+        tokens have been read back: the ids are gathered on the device (b200_gather_tokens)."""
         n = len(seqs)
         if staged is None:
             k = self.stage_decode(seqs)
@@ -335,9 +341,13 @@ class ModelRunner:
             k = staged
             self.hd[k]["ids"][:n] = np.fromiter((s.last_token for s in seqs), dtype=np.int64, count=n)
         self.hd[k]["step"][0] = self.sample_step
+        if src is not None:
+            self.hd[k]["src"][:n] = src
         nbytes = self.d_off["bt"] + padded * self.max_blocks * 4
         self.stage.upload(nbytes, k)
         self.h2d_bytes_last = nbytes
+        if src is not None:
+            ops.gather_tokens(self.g_ids[:n], self.g_src[:n], self.g_tokens)
         set_context(False, slot_mapping=self.g_slot[:padded], context_lens=self.g_ctx[:padded],
                     block_tables=self.g_bt[:padded])
 
@@ -360,8 +370,9 @@ class ModelRunner:
         return self.collect()
 
     @torch.inference_mode()
-    def launch(self, seqs: list[Sequence], is_prefill: bool, staged: int | None = None) -> None:
-        """Enqueue one step (metadata upload, forward, sampling, token read-back) without waiting for it."""
+    def launch(self, seqs: list[Sequence], is_prefill: bool, staged: int | None = None, src=None) -> None:
+        """Enqueue one step (metadata upload, forward, sampling, token read-back) without waiting for it.
+        Up to two steps may be in flight; collect() returns them in launch order."""
         n = len(seqs)
         self.sample_step += 1
         prof = self._prof
@@ -376,7 +387,7 @@ class ModelRunner:
             if n > self.cap_bs:
                 raise RuntimeError(f"decode batch {n} exceeds max_num_seqs = {self.cap_bs}")
             padded = self._padded_rows(n)
-            self.prepare_decode(seqs, padded, staged)
+            self.prepare_decode(seqs, padded, staged, src)
             if prof is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
@@ -392,16 +403,20 @@ class ModelRunner:
             prof["h2d"] += self.h2d_bytes_last
             prof["d2h"] += n * 8
             prof["steps"] += 1
-        self.h_tokens[:n].copy_(self.g_tokens[:n], non_blocking=True)
-        self._done.record()
-        self._inflight = n
+        kk = self._launches & 1
+        self._launches += 1
+        assert len(self._pending) < 2, "at most two steps in flight"
+        self.h_tokens[kk][:n].copy_(self.g_tokens[:n], non_blocking=True)
+        self._done[kk].record()
+        self._pending.append((kk, n))
         self.d2h_bytes_last = n * 8
+        reset_context()
 
     def collect(self) -> list[int]:
-        """Wait for the step enqueued by launch() (the step's only host sync) and return its token ids."""
-        self._done.synchronize()
-        reset_context()
-        return self.h_tokens_np[:self._inflight].tolist()
+        """Wait for the oldest step enqueued by launch() (that step's only host sync) and return its token ids."""
+        kk, n = self._pending.popleft()
+        self._done[kk].synchronize()
+        return self.h_tokens_np[kk][:n].tolist()
 
     @torch.inference_mode()
     def capture_cudagraph(self):

@@ -183,6 +183,14 @@ def embedding(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor | None =
     return out
 
 
+def gather_tokens(ids: torch.Tensor, src: torch.Tensor, prev_tokens: torch.Tensor) -> torch.Tensor:
+    """ids[i] = prev_tokens[src[i]] where src[i] >= 0 (in place)."""
+    _need(ids, torch.int64, "ids"); _need(src, torch.int32, "src"); _need(prev_tokens, torch.int64, "prev_tokens")
+    lib = nat.load()
+    nat.check(lib.b200_gather_tokens(ids.data_ptr(), src.data_ptr(), prev_tokens.data_ptr(), ids.numel(), _stream()))
+    return ids
+
+
 def sample(logits: torch.Tensor, temperatures: torch.Tensor | None, seed: int, step: int,
            out: torch.Tensor | None = None, index_offset: int = 0, out_keys: torch.Tensor | None = None,
            step_dev: torch.Tensor | None = None) -> torch.Tensor:

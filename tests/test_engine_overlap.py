@@ -19,8 +19,9 @@ class FakeRunner:
         self.build = product_meta_builder(block_size)
         self.vocab = vocab
         self.steps = []
-        self.pending = None
+        self.queue = []
         self.staged = 0
+        self.early = 0
 
     def call(self, name, *a):
         return getattr(self, name)(*a)
@@ -29,15 +30,28 @@ class FakeRunner:
         self.staged += 1
         return 0
 
-    def launch(self, seqs, is_prefill, staged=None):
-        # at launch every token value a step consumes must be known (no placeholder left in its inputs)
+    def launch(self, seqs, is_prefill, staged=None, src=None):
+        # every token value a step consumes must be known at launch, or named by `src` as a row of the step
+        # still in flight (the device-side gather); emulate the gather to record what the model would see
         meta = self.build(seqs, is_prefill)
-        assert (meta["input_ids"] >= 0).all(), "placeholder token reached the model input"
+        ids = meta["input_ids"].copy()
+        if src is not None:
+            assert not is_prefill and len(self.queue) == 1, "early launch only for a decode step behind one running step"
+            prev = self.queue[0]
+            for i, r in enumerate(src):
+                if r >= 0:
+                    assert ids[i] == -1
+                    ids[i] = prev[r]
+            self.early += 1
+        assert (ids >= 0).all(), "placeholder token reached the model input"
+        meta["input_ids"] = ids
         self.steps.append(step_record(seqs, is_prefill, meta))
-        self.pending = [fake_token(s.seq_id, len(s), self.vocab) for s in seqs]
+        # the fake model's token depends on the sequence length only, which is already final
+        self.queue.append([fake_token(s.seq_id, len(s), self.vocab) for s in seqs])
+        assert len(self.queue) <= 2
 
     def collect(self):
-        return self.pending
+        return self.queue.pop(0)
 
 
 @pytest.mark.parametrize("name", ["prefix16", "chunked32", "eos64", "bench_tight"])
@@ -69,7 +83,7 @@ def test_overlapped_loop_equals_reference_trace(name, golden_dir):
     for i, (a, b) in enumerate(zip(got, gold["steps"])):
         assert a == b, f"step {i}: overlapped {a} != reference {b}"
     assert digest(*[np.asarray(outputs[k]) for k in sorted(outputs)]) == gold["outputs"]
-    if w["sps"][0][2]:          # ignore_eos workloads take the early-staging path
-        assert eng.model_runner.staged > 0
+    if w["sps"][0][2]:          # ignore_eos workloads enqueue decode steps early
+        assert eng.model_runner.early > 0
     else:
-        assert eng.model_runner.staged == 0
+        assert eng.model_runner.early == 0
