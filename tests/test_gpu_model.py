@@ -104,6 +104,57 @@ def test_engine_greedy_generate_vs_oracle(tiny_dir, eager):
     record("engine_greedy", dict(eager=eager, tokens=tot, differ_from_oracle_argmax=diff, worst_margin_over_tol=worst))
 
 
+def test_engine_chunked_prefill_and_preemption(tiny_dir):
+    """Prompts longer than max_num_batched_tokens (chunked prefill through the paged path) and a KV cache too small
+    for the whole batch (preemption + re-prefill through the prefix cache), greedy, checked against the oracle."""
+    from nanovllm import LLM, SamplingParams
+    from nanovllm.utils.synthetic import PRESETS, random_weights
+    rnd = random.Random(11)
+    vocab = PRESETS["tiny"]["vocab_size"]
+    prompts = [[rnd.randint(2, vocab - 1) for _ in range(n)] for n in (200, 150, 33, 90, 64, 17)]
+    sps = [SamplingParams(temperature=0.0, max_tokens=40, ignore_eos=True) for _ in prompts]
+    llm = LLM(tiny_dir, max_model_len=256, max_num_seqs=6, max_num_batched_tokens=64, kvcache_block_size=16, num_kvcache_blocks=40)
+    try:
+        outs = llm.generate(prompts, sps, use_tqdm=False)
+        assert len(llm.scheduler.block_manager.used_block_ids) == 0
+    finally:
+        llm.exit()
+    oracle = make_oracle(PRESETS["tiny"], random_weights(PRESETS["tiny"], seed=1234), "fused")
+    tot = diff = 0
+    for p, o in zip(prompts, outs):
+        assert len(o["token_ids"]) == 40
+        n, d, _ = check_greedy_against_oracle(oracle, p, o["token_ids"])
+        tot, diff = tot + n, diff + d
+    record("engine_chunked_preempt", dict(tokens=tot, differ_from_oracle_argmax=diff))
+
+
+def test_prefill_bench_size_rows_vs_oracle():
+    """BASELINE config-2 prefill shape (Hq16/Hkv8, prompts up to 1024 tokens, ~16k tokens per step): a few whole
+    sequences against the oracle, the rest through a property -- every sequence's output is independent of its
+    neighbours in the batch."""
+    from nanovllm import ops
+    from oracle.paged_attention_ref import varlen_prefill_ref
+    from oracle.make_golden import workloads
+    from test_gpu_kernels import assert_close_bf16
+    lens = [len(p) for p in workloads()["bench"]["prompts"][:31]]
+    tot = sum(lens)
+    assert tot == 15705
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(tot, 32 * 128, generator=g).to(torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    dev = qkv.cuda()
+    q, k, v = dev[:, :2048].view(tot, 16, 128), dev[:, 2048:3072].view(tot, 8, 128), dev[:, 3072:].view(tot, 8, 128)
+    out = ops.paged_prefill(0, q, k, v, cu.cuda(), cu.cuda(), max(lens), max(lens), 128 ** -0.5).cpu()
+    for s in (0, 7, 30):
+        a, b = int(cu[s]), int(cu[s + 1])
+        c2 = torch.tensor([0, b - a], dtype=torch.int32)
+        want = varlen_prefill_ref(qkv[a:b, :2048].view(-1, 16, 128), qkv[a:b, 2048:3072].view(-1, 8, 128),
+                                  qkv[a:b, 3072:].view(-1, 8, 128), c2, c2, 128 ** -0.5, p_dtype=torch.bfloat16)
+        assert_close_bf16(out[a:b], want, f"bench-size prefill seq {s}")
+        alone = ops.paged_prefill(0, q[a:b], k[a:b], v[a:b], c2.cuda(), c2.cuda(), b - a, b - a, 128 ** -0.5).cpu()
+        assert torch.equal(alone, out[a:b]), "a sequence's output must not depend on its batch neighbours"
+
+
 def test_engine_sampling_and_eos(tiny_dir):
     from nanovllm import LLM, SamplingParams
     llm = LLM(tiny_dir, max_model_len=128, max_num_seqs=4, kvcache_block_size=32, num_kvcache_blocks=32)
