@@ -92,6 +92,20 @@ int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0
                       void* out, int64_t out_stride0, int batch, int num_q_heads, float scale,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* One-launch decode layer front end: what Qwen3Attention.forward does between the qkv GEMM and o_proj for a decode
+ * step (models/qwen3.py:77-86 + layers/attention.py:62-63,71-74): q_norm / k_norm (RMSNorm over head_dim, rounded
+ * to bf16), NeoX RoPE at position context_lens[b]-1 (cos_sin: fp32 [max_pos, head_dim] = cat(cos, sin)), the step's
+ * K/V row appended to slot block_tables[b, (ctx-1)/block_size]*block_size + (ctx-1)%block_size of `layer` -- the slot
+ * ModelRunner.prepare_decode computes (model_runner.py:181) -- and attention over keys 0..ctx-1.
+ * qkv: the raw fused projection output [batch, (num_q_heads + 2*num_kv_heads) * head_dim] bf16 (not modified).
+ * Same result as b200_qknorm_rope_store followed by b200_paged_decode, one kernel instead of two. */
+int b200_paged_decode_fused(b200_ctx* ctx, int layer, const void* qkv, int64_t qkv_stride0,
+                            const void* q_norm_weight, const void* k_norm_weight, const float* cos_sin,
+                            float eps, const int32_t* block_tables, int bt_stride,
+                            const int32_t* context_lens, void* out, int64_t out_stride0, int batch,
+                            int num_q_heads, float scale, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* Prefill branch of Attention.forward (layers/attention.py:64-70), i.e.
  * flash_attn_varlen_func(q, k, v, cu_seqlens_q/k, max_seqlen_q/k, softmax_scale=scale,
  * causal=True, block_table=block_tables): bottom-right aligned causal mask, query i of a

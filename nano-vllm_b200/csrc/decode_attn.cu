@@ -48,12 +48,22 @@ struct DecodeParams {
     float* part_o;    // [slots][G][128]
     float* part_ml;   // [slots][G][2]
     int* counters;    // [batch * hkv], zero on entry, zero on exit
+    // fused mode (b200_paged_decode_fused): q points at the raw qkv GEMM output; the kernel itself applies
+    // q/k RMSNorm + RoPE and appends the step's K/V row to the cache
+    const __nv_bfloat16* q_norm_w;
+    const __nv_bfloat16* k_norm_w;
+    const float* cos_sin;
+    __nv_bfloat16* k_layer_w;   // writable aliases of k_layer / v_layer
+    __nv_bfloat16* v_layer_w;
+    float eps;
 };
 
-template <int G, int NWARPS, int NSTAGES>
+constexpr int CS_BYTES = B200_HEAD_DIM * 4;        // one cos|sin row of the rotary table
+
+template <int G, int NWARPS, int NSTAGES, bool FUSED = false>
 struct DecodeSmem {
     static constexpr int kQBytes = G * ROW_BYTES;                        // the G query heads of one kv head
-    static constexpr int kStageBytes = 2 * CHUNK_BYTES + kQBytes;       // [K chunk][V chunk][q of the segment]
+    static constexpr int kStageBytes = 2 * CHUNK_BYTES + kQBytes + (FUSED ? CS_BYTES : 0);   // [K][V][q][cos|sin]
     static constexpr int kWarpBytes = NSTAGES * kStageBytes;
     static constexpr int kOffStages = 0;
     static constexpr int kOffCum = NWARPS * kWarpBytes;                 // int[MAX_BATCH + 1]
@@ -91,9 +101,9 @@ struct ChunkCursor {
     }
 };
 
-template <int G, int NWARPS, int NSTAGES>
+template <int G, int NWARPS, int NSTAGES, bool FUSED>
 __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const DecodeParams p) {
-    using L = DecodeSmem<G, NWARPS, NSTAGES>;
+    using L = DecodeSmem<G, NWARPS, NSTAGES, FUSED>;
     extern __shared__ __align__(128) uint8_t smem[];
     int* cum = reinterpret_cast<int*>(smem + L::kOffCum);
     int* ctxs = reinterpret_cast<int*>(smem + L::kOffCtx);
@@ -204,16 +214,22 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
             const int page = pg_next;
             int valid = pi.ctx - tok0;
             valid = valid > CHUNK ? CHUNK : valid;
+            if (FUSED && pi.ck == pi.n - 1) --valid;              // the newest token is not in the cache yet
             const uint32_t bytes = (uint32_t)valid * ROW_BYTES;
             const int64_t row = (((int64_t)page * hkv + pi.h) << p.block_shift) + (tok0 & bs_mask);
             const uint32_t bar = my_bars_u32 + slot * 8;
             const uint32_t dst = my_stages_u32 + slot * L::kStageBytes;
             const bool seg_first = (pi.ck == 0) || (i == 0);      // the consumer starts a segment on this chunk
-            mbar_expect_tx(bar, 2 * bytes + (seg_first ? (uint32_t)L::kQBytes : 0u));
-            bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
-            bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
-            if (seg_first)
+            mbar_expect_tx(bar, 2 * bytes + (seg_first ? (uint32_t)(L::kQBytes + (FUSED ? CS_BYTES : 0)) : 0u));
+            if (bytes) {
+                bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
+                bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
+            }
+            if (seg_first) {
                 bulk_g2s(dst + 2 * CHUNK_BYTES, p.q + (int64_t)pi.b * p.q_stride + pi.h * G * B200_HEAD_DIM, L::kQBytes, bar);
+                if (FUSED)
+                    bulk_g2s(dst + 2 * CHUNK_BYTES + L::kQBytes, p.cos_sin + (int64_t)(pi.ctx - 1) * B200_HEAD_DIM, CS_BYTES, bar);
+            }
         }
         pi.advance(cum, ctxs, batch, hkv);
         if (lane == 0 && i + 1 < n_local)
@@ -228,6 +244,30 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     float o[G][8];
     float m[G], l[G];
     bool seg_start = true;
+    // fused mode: this lane's slice of the q/k norm weights (whole kernel) and of the cos|sin row (per segment)
+    float qw[8], kw[8], cosr[8], sinr[8];
+    if (FUSED) {
+        unpack8(*reinterpret_cast<const uint4*>(p.q_norm_w + j * 8), qw);
+        unpack8(*reinterpret_cast<const uint4*>(p.k_norm_w + j * 8), kw);
+    }
+    // RMSNorm over head_dim (the 16 lanes of a half-warp hold one head) -> bf16 -> NeoX rotation -> bf16, the
+    // arithmetic of qknorm_rope_store_kernel (models/qwen3.py:82-85)
+    auto norm_rope = [&](float (&x)[8], const float (&w)[8]) {
+        float ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+#pragma unroll
+        for (int o2 = 8; o2 > 0; o2 >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o2);
+        const float rstd = 1.0f / sqrtf(ss / (float)B200_HEAD_DIM + p.eps);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float y = round_bf16(__fmul_rn(__fmul_rn(x[e], rstd), w[e]));
+            const float other = __shfl_xor_sync(0xffffffffu, y, 8);          // element d +- 64
+            const float r = (j < 8) ? __fsub_rn(__fmul_rn(y, cosr[e]), __fmul_rn(other, sinr[e]))
+                                    : __fadd_rn(__fmul_rn(y, cosr[e]), __fmul_rn(other, sinr[e]));
+            x[e] = round_bf16(r);
+        }
+    };
 
 #pragma unroll 1
     for (int i = 0; i < n_local; ++i) {
@@ -238,18 +278,41 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
         const uint8_t* ks = my_stages + slot * L::kStageBytes;
         const uint8_t* vs = ks + CHUNK_BYTES;
 
+        // fused mode: the raw K / V row of the newest token is needed after the last chunk of the kv head;
+        // start its loads now so they fly under the chunk's math
+        const bool last_chunk = FUSED && (ci.ck == ci.n - 1);
+        uint4 k_raw = make_uint4(0, 0, 0, 0), v_raw = make_uint4(0, 0, 0, 0);
+        if (last_chunk) {
+            const __nv_bfloat16* rowp = p.q + (int64_t)ci.b * p.q_stride + j * 8;
+            k_raw = *reinterpret_cast<const uint4*>(rowp + (hkv * G + ci.h) * B200_HEAD_DIM);
+            v_raw = *reinterpret_cast<const uint4*>(rowp + (hkv * G + hkv + ci.h) * B200_HEAD_DIM);
+        }
+
         if (seg_start) {                                  // q arrived with this chunk
             seg_start = false;
+            if (FUSED) {
+                const float* cs = reinterpret_cast<const float*>(ks + 2 * CHUNK_BYTES + L::kQBytes) + (j & 7) * 8;
+                const float4 c0 = *reinterpret_cast<const float4*>(cs), c1 = *reinterpret_cast<const float4*>(cs + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(cs + 64), s1 = *reinterpret_cast<const float4*>(cs + 68);
+                cosr[0] = c0.x; cosr[1] = c0.y; cosr[2] = c0.z; cosr[3] = c0.w; cosr[4] = c1.x; cosr[5] = c1.y; cosr[6] = c1.z; cosr[7] = c1.w;
+                sinr[0] = s0.x; sinr[1] = s0.y; sinr[2] = s0.z; sinr[3] = s0.w; sinr[4] = s1.x; sinr[5] = s1.y; sinr[6] = s1.z; sinr[7] = s1.w;
+            }
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const uint4 w = *reinterpret_cast<const uint4*>(ks + 2 * CHUNK_BYTES + g * ROW_BYTES + j * 16);
                 unpack8(w, qf[g]);
+                if (FUSED) norm_rope(qf[g], qw);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { qf[g][e] *= p.scale_log2; o[g][e] = 0.f; }
                 m[g] = -INFINITY;
                 l[g] = 0.f;
             }
         }
+
+        int nvalid = ci.ctx - ci.ck * CHUNK;
+        nvalid = nvalid > CHUNK ? CHUNK : nvalid;
+        if (last_chunk) --nvalid;                         // the newest token is handled from registers below
+        if (nvalid > 0) {
 
         // ---- S = q K^T : half-warp per token, 16 lanes x 8 dims ---------------------------------
         float acc[G][8];
@@ -291,8 +354,6 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
         // this lane now holds the score of token  t = 2*it + hw,  it = bits (3,2,1) of j
         const int my_it = ((j >> 3) & 1) * 4 + ((j >> 2) & 1) * 2 + ((j >> 1) & 1);
         const int my_t = 2 * my_it + hw;
-        int nvalid = ci.ctx - ci.ck * CHUNK;
-        nvalid = nvalid > CHUNK ? CHUNK : nvalid;
         const bool tok_ok = my_t < nvalid;
 
         // ---- online softmax ---------------------------------------------------------------------
@@ -339,6 +400,38 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
             }
         };
         if (nvalid == CHUNK) pv(std::false_type{}); else pv(std::true_type{});
+        }   // nvalid > 0
+
+        if (last_chunk) {
+            // ---- the step's own token: k = rope(norm(k_raw)), v = v_raw, appended to the cache and attended ----
+            float kn[8], vn[8];
+            unpack8(k_raw, kn);
+            unpack8(v_raw, vn);
+            norm_rope(kn, kw);
+            const int tok = ci.ctx - 1;
+            const int page = p.block_tables[(int64_t)ci.b * p.bt_stride + (tok >> p.block_shift)];
+            const int64_t crow = (((int64_t)page * hkv + ci.h) << p.block_shift) + (tok & bs_mask);
+            if (hw == 0) {
+                *reinterpret_cast<uint4*>(p.k_layer_w + crow * B200_HEAD_DIM + j * 8) = pack8(kn);
+                *reinterpret_cast<uint4*>(p.v_layer_w + crow * B200_HEAD_DIM + j * 8) = v_raw;
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float sc = qf[g][0] * kn[0];
+#pragma unroll
+                for (int e = 1; e < 8; ++e) sc = fmaf(qf[g][e], kn[e], sc);
+#pragma unroll
+                for (int o2 = 8; o2 > 0; o2 >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o2);
+                const float m_new = fmaxf(m[g], sc);
+                const float alpha = fast_exp2(m[g] - m_new);
+                const float pn = fast_exp2(sc - m_new);
+                m[g] = m_new;
+                l[g] = l[g] * alpha + (lane == 0 ? pn : 0.f);
+                const float pv0 = hw == 0 ? pn : 0.f;        // the two half-warps' partial O are summed at the end
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pv0, vn[e], o[g][e] * alpha);
+            }
+        }
         __syncwarp();   // every lane is done with this stage and with pbuf
 
         // ---- end of a segment (kv head exhausted, or this warp's range ends) ---------------------
@@ -447,13 +540,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
 constexpr int kMaxWarps = 16;   // workspace is sized for the widest variant
 
 // (warps per CTA, ring depth) variants; B200_DECODE_CFG=<warps>x<stages> picks one at first use (tuning knob).
-template <int G, int NW, int NS>
+template <int G, int NW, int NS, bool FUSED>
 int launch_variant(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
-    using L = DecodeSmem<G, NW, NS>;
+    using L = DecodeSmem<G, NW, NS, FUSED>;
     if constexpr (L::kTotal > 227 * 1024) {
         return B200_EUNSUPPORTED;
     } else {
-        auto kern = paged_decode_kernel<G, NW, NS>;
+        auto kern = paged_decode_kernel<G, NW, NS, FUSED>;
         static bool configured = false;
         if (!configured) {
             B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -473,27 +566,23 @@ int decode_variant() {
         if (e && !strcmp(e, "10x2")) v = 2;
         if (e && !strcmp(e, "8x3")) v = 3;
         if (e && !strcmp(e, "6x2")) v = 4;
-        if (e && !strcmp(e, "4x2")) v = 5;
-        if (e && !strcmp(e, "6x3")) v = 6;
-        if (e && !strcmp(e, "4x3")) v = 7;
     }
     return v;
 }
 
-template <int G>
+template <int G, bool FUSED>
 int launch_decode(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
     if constexpr (G == 8) {
-        return launch_variant<G, 8, 2>(ctx, prm, stream);     // 3 stages of 10 KB x 8 warps exceed 227 KB
+        return launch_variant<G, 8, 2, FUSED>(ctx, prm, stream);     // 3 stages of 10 KB x 8 warps exceed 227 KB
+    } else if constexpr (FUSED) {
+        return launch_variant<G, 8, 2, true>(ctx, prm, stream);
     } else {
         switch (decode_variant()) {
-            case 1: return launch_variant<G, 12, 2>(ctx, prm, stream);
-            case 2: return launch_variant<G, 10, 2>(ctx, prm, stream);
-            case 3: return launch_variant<G, 8, 3>(ctx, prm, stream);
-            case 4: return launch_variant<G, 6, 2>(ctx, prm, stream);
-            case 5: return launch_variant<G, 4, 2>(ctx, prm, stream);
-            case 6: return launch_variant<G, 6, 3>(ctx, prm, stream);
-            case 7: return launch_variant<G, 4, 3>(ctx, prm, stream);
-            default: return launch_variant<G, 8, 2>(ctx, prm, stream);
+            case 1: return launch_variant<G, 12, 2, false>(ctx, prm, stream);
+            case 2: return launch_variant<G, 10, 2, false>(ctx, prm, stream);
+            case 3: return launch_variant<G, 8, 3, false>(ctx, prm, stream);
+            case 4: return launch_variant<G, 6, 2, false>(ctx, prm, stream);
+            default: return launch_variant<G, 8, 2, false>(ctx, prm, stream);
         }
     }
 }
@@ -523,11 +612,10 @@ extern "C" size_t b200_decode_workspace_bytes(const b200_ctx* ctx, int max_batch
     return ws_layout(ctx->sm_count, max_batch, ctx->num_kv_heads, num_q_heads / ctx->num_kv_heads).total;
 }
 
-extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0,
-                                 const int32_t* block_tables, int bt_stride,
-                                 const int32_t* context_lens, void* out, int64_t out_stride0,
-                                 int batch, int num_q_heads, float scale, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+static int decode_common(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0, const int32_t* block_tables,
+                         int bt_stride, const int32_t* context_lens, void* out, int64_t out_stride0, int batch,
+                         int num_q_heads, float scale, void* workspace, size_t workspace_bytes, void* stream,
+                         const void* q_norm_w, const void* k_norm_w, const float* cos_sin, float eps, bool fused) {
     if (!ctx || !q || !out || !block_tables || !context_lens || !workspace) return B200_EINVAL;
     if (!ctx->k_base) return B200_ENOTBOUND;
     if (layer < 0 || layer >= ctx->layers || batch < 0) return B200_EINVAL;
@@ -538,6 +626,9 @@ extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_
     const int G = num_q_heads / hkv;
     if (G != 1 && G != 2 && G != 4 && G != 8) return B200_EUNSUPPORTED;
     if ((q_stride0 % 8) || (out_stride0 % 8) || ((uintptr_t)q % 16) || ((uintptr_t)out % 16)) return B200_EINVAL;
+    if (fused && (!q_norm_w || !k_norm_w || !cos_sin || ((uintptr_t)q_norm_w % 16) || ((uintptr_t)k_norm_w % 16) ||
+                  ((uintptr_t)cos_sin % 16)))
+        return B200_EINVAL;
     const WsLayout w = ws_layout(ctx->sm_count, batch, hkv, G);
     if (workspace_bytes < w.total) return B200_EWORKSPACE;
 
@@ -548,6 +639,8 @@ extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_
     prm.out_stride = out_stride0;
     prm.k_layer = ctx->k_layer(layer);
     prm.v_layer = ctx->v_layer(layer);
+    prm.k_layer_w = ctx->k_layer(layer);
+    prm.v_layer_w = ctx->v_layer(layer);
     prm.block_tables = block_tables;
     prm.bt_stride = bt_stride;
     prm.context_lens = context_lens;
@@ -555,15 +648,47 @@ extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_
     prm.hkv = hkv;
     prm.block_shift = ctx->block_shift;
     prm.scale_log2 = scale * 1.4426950408889634f;
+    prm.q_norm_w = static_cast<const __nv_bfloat16*>(q_norm_w);
+    prm.k_norm_w = static_cast<const __nv_bfloat16*>(k_norm_w);
+    prm.cos_sin = cos_sin;
+    prm.eps = eps;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     prm.counters = reinterpret_cast<int*>(ws);
     prm.part_ml = reinterpret_cast<float*>(ws + w.off_ml);
     prm.part_o = reinterpret_cast<float*>(ws + w.off_o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (G) {
-        case 1: return launch_decode<1>(ctx, prm, st);
-        case 2: return launch_decode<2>(ctx, prm, st);
-        case 4: return launch_decode<4>(ctx, prm, st);
-        default: return launch_decode<8>(ctx, prm, st);
+    if (fused) {
+        switch (G) {
+            case 1: return launch_decode<1, true>(ctx, prm, st);
+            case 2: return launch_decode<2, true>(ctx, prm, st);
+            case 4: return launch_decode<4, true>(ctx, prm, st);
+            default: return launch_decode<8, true>(ctx, prm, st);
+        }
     }
+    switch (G) {
+        case 1: return launch_decode<1, false>(ctx, prm, st);
+        case 2: return launch_decode<2, false>(ctx, prm, st);
+        case 4: return launch_decode<4, false>(ctx, prm, st);
+        default: return launch_decode<8, false>(ctx, prm, st);
+    }
+}
+
+extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0,
+                                 const int32_t* block_tables, int bt_stride,
+                                 const int32_t* context_lens, void* out, int64_t out_stride0,
+                                 int batch, int num_q_heads, float scale, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    return decode_common(ctx, layer, q, q_stride0, block_tables, bt_stride, context_lens, out, out_stride0, batch,
+                         num_q_heads, scale, workspace, workspace_bytes, stream, nullptr, nullptr, nullptr, 0.f, false);
+}
+
+extern "C" int b200_paged_decode_fused(b200_ctx* ctx, int layer, const void* qkv, int64_t qkv_stride0,
+                                       const void* q_norm_weight, const void* k_norm_weight,
+                                       const float* cos_sin, float eps, const int32_t* block_tables,
+                                       int bt_stride, const int32_t* context_lens, void* out,
+                                       int64_t out_stride0, int batch, int num_q_heads, float scale,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+    return decode_common(ctx, layer, qkv, qkv_stride0, block_tables, bt_stride, context_lens, out, out_stride0, batch,
+                         num_q_heads, scale, workspace, workspace_bytes, stream, q_norm_weight, k_norm_weight, cos_sin,
+                         eps, true);
 }

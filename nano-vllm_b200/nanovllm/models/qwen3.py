@@ -6,6 +6,7 @@ inside them.  Per layer and per step this issues
 
     add_rmsnorm -> qkv GEMM -> [q/k-norm + RoPE + KV scatter] -> paged attention -> o GEMM (+all-reduce)
     -> add_rmsnorm -> gate_up GEMM -> silu*mul -> down GEMM (+all-reduce)
+(in a decode step the bracket and the attention are one kernel, b200_paged_decode_fused)
 
 GEMMs are library calls (cuBLAS through ``F.linear``, as in the reference, linear.py:51,73,153);
 everything else is one hand-written kernel from libb200attn.  Tensor parallelism shards heads and
@@ -155,13 +156,18 @@ class Qwen3ForCausalLM:
                 x, residual = ops.add_rmsnorm(h, residual, L.ln1, eps)
             qkv = F.linear(x, L.qkv)
             cached = attn.k_cache.numel() > 0
-            ops.qknorm_rope_store(li, qkv, hq, hkv, positions, L.q_norm, L.k_norm, self.cos_sin, eps,
-                                  ctx.slot_mapping if cached else None)
             t = qkv.shape[0]
-            q = qkv[:, :self.q_size].view(t, hq, d)
-            k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
-            v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
-            o = attn(q, k, v, kv_stored=True)
+            if cached and not ctx.is_prefill:
+                # decode: q/k-norm, RoPE, KV append and attention in ONE launch on the raw projection output
+                o = ops.paged_decode_fused(li, qkv, hq, L.q_norm, L.k_norm, self.cos_sin, eps, ctx.block_tables,
+                                           ctx.context_lens, attn.scale)
+            else:
+                ops.qknorm_rope_store(li, qkv, hq, hkv, positions, L.q_norm, L.k_norm, self.cos_sin, eps,
+                                      ctx.slot_mapping if cached else None)
+                q = qkv[:, :self.q_size].view(t, hq, d)
+                k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
+                v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
+                o = attn(q, k, v, kv_stored=True)
             h = self._all_reduce(F.linear(o.reshape(t, self.q_size), L.o))
             x, residual = ops.add_rmsnorm(h, residual, L.ln2, eps)
             h = self._all_reduce(F.linear(ops.silu_mul(F.linear(x, L.gate_up)), L.down))

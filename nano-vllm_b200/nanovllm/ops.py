@@ -88,6 +88,26 @@ def paged_decode(layer: int, q: torch.Tensor, block_tables: torch.Tensor, contex
     return out
 
 
+def paged_decode_fused(layer: int, qkv: torch.Tensor, num_q_heads: int, q_norm_weight, k_norm_weight, cos_sin: torch.Tensor,
+                       eps: float, block_tables: torch.Tensor, context_lens: torch.Tensor, scale: float,
+                       out: torch.Tensor | None = None) -> torch.Tensor:
+    """Raw qkv GEMM output [B, (Hq+2Hkv)*D] -> attention output [B, Hq, D]; q/k-norm, RoPE and the KV append happen
+    inside the decode kernel (qkv itself is left untouched)."""
+    _need(qkv, torch.bfloat16, "qkv"); _need(block_tables, torch.int32, "block_tables"); _need(context_lens, torch.int32, "context_lens")
+    _need(cos_sin, torch.float32, "cos_sin")
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and block_tables.stride(1) == 1
+    b = qkv.shape[0]
+    if out is None:
+        out = torch.empty((b, num_q_heads, 128), dtype=qkv.dtype, device=qkv.device)
+    ws = ensure_workspace(b, num_q_heads)
+    h = nat.handle()
+    nat.check(h.lib.b200_paged_decode_fused(h.ptr, layer, qkv.data_ptr(), qkv.stride(0), q_norm_weight.data_ptr(),
+                                            k_norm_weight.data_ptr(), cos_sin.data_ptr(), eps, block_tables.data_ptr(),
+                                            block_tables.stride(0), context_lens.data_ptr(), out.data_ptr(), out.stride(0),
+                                            b, num_q_heads, scale, ws.data_ptr(), ws.numel(), _stream()), h.ptr)
+    return out
+
+
 def paged_prefill(layer: int, q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q: int, max_seqlen_k: int,
                   scale: float, block_tables=None, num_kv_heads: int | None = None, out=None) -> torch.Tensor:
     """q [T, Hq, D]; k, v [Tk, Hkv, D] (ignored when block_tables is given)."""

@@ -161,6 +161,52 @@ def test_paged_decode_page_permutation_invariance(ops):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("hq,hkv,bs,lens", [(16, 8, 256, [1, 16, 17, 300, 1024, 0, 33, 2048]), (8, 2, 16, [5, 16, 49, 1]),
+                                            (8, 1, 64, [65, 64, 700]), (4, 4, 32, [31, 32, 33])])
+def test_paged_decode_fused_vs_two_kernels_and_oracle(ops, hq, hkv, bs, lens):
+    """b200_paged_decode_fused == b200_qknorm_rope_store + b200_paged_decode == the oracle, including what ends up in
+    the cache for the step's own token (position ctx-1, slot from the block table)."""
+    nblk = sum((c + bs - 1) // bs for c in lens) + 2
+    tables = make_tables(lens, bs, nblk, seed=12)
+    ctx = torch.tensor(lens, dtype=torch.int32)
+    n = len(lens)
+    qkv = bf(n, (hq + 2 * hkv) * 128, seed=17)
+    qw, kw = (1 + 0.1 * torch.randn(128)).to(torch.bfloat16), (1 + 0.1 * torch.randn(128)).to(torch.bfloat16)
+    table = rope_table(128, 4096, 1e6)
+    pos = (ctx.long() - 1).clamp(min=0)
+    slots = torch.tensor([(int(tables[i, (c - 1) // bs]) * bs + (c - 1) % bs) if c > 0 else -1 for i, c in enumerate(lens)],
+                         dtype=torch.int32)
+    scale = 128 ** -0.5
+    # oracle: norm + rope on q/k, scatter, attend
+    kv, ks, vs = bind_random_cache(ops, 1, nblk, hkv, bs, seed=71)
+    q = qkv[:, :hq * 128].view(n, hq, 128)
+    k = qkv[:, hq * 128:(hq + hkv) * 128].view(n, hkv, 128)
+    v = qkv[:, (hq + hkv) * 128:].view(n, hkv, 128)
+    q_o = rope_ref(table, pos, rmsnorm_ref(q, qw, 1e-6))
+    k_o = rope_ref(table, pos, rmsnorm_ref(k, kw, 1e-6))
+    ko, vo = ks[0].clone(), vs[0].clone()
+    store_kvcache_ref(k_o, v, ko, vo, slots)
+    want = paged_decode_ref(q_o, ko, vo, ctx, tables, scale)
+    # two kernels
+    g2 = qkv.cuda()
+    ops.qknorm_rope_store(0, g2, hq, hkv, pos.cuda(), qw.cuda(), kw.cuda(), table.cuda(), 1e-6, slots.cuda())
+    two = ops.paged_decode(0, g2[:, :hq * 128].view(n, hq, 128), tables.cuda(), ctx.cuda(), scale)
+    cache_two = kv.clone()
+    # fused, on a pristine copy of the cache
+    kv2, _, _ = bind_random_cache(ops, 1, nblk, hkv, bs, seed=71)
+    g1 = qkv.cuda()
+    fused = ops.paged_decode_fused(0, g1, hq, qw.cuda(), kw.cuda(), table.cuda(), 1e-6, tables.cuda(), ctx.cuda(), scale)
+    assert torch.equal(g1.cpu(), qkv), "the fused kernel must not modify the projection output"
+    assert_close_bf16(fused, want, "fused decode vs oracle")
+    assert_close_bf16(fused, two, "fused decode vs two-kernel path", ulps=1.01, rel_l2=2e-3)
+    assert torch.equal(kv2[1], cache_two[1]), "V rows are plain copies: bit-exact"
+    assert_close_bf16(kv2[0], cache_two[0], "appended K rows", ulps=1.01, rel_l2=1e-3)
+    assert_close_bf16(to_logical(kv2[0, 0].cpu()), ko, "cache K vs oracle", ulps=1.01, rel_l2=1e-3)
+    for i, c in enumerate(lens):
+        if c == 0:
+            assert fused[i].float().abs().max().item() == 0.0
+
+
 # ---------------------------------------------------------------------------------------------
 # K2/K3 prefill
 # ---------------------------------------------------------------------------------------------
