@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--hq", type=int, default=16)
     ap.add_argument("--hkv", type=int, default=8)
     ap.add_argument("--ncu", action="store_true", help="one launch per step inside a cudaProfiler window")
+    ap.add_argument("--fused", action="store_true", help="time b200_paged_decode_fused (raw qkv in) against qknorm_rope_store + paged_decode")
     args = ap.parse_args()
     from nanovllm import ops
     steps = [int(x) for x in args.steps.split(",")]
@@ -79,6 +80,38 @@ def main():
             ops.paged_decode(0, q, bt, ctx, 0.0884, out=out)
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
+            continue
+        if args.fused:
+            from nanovllm.layers.rotary_embedding import build_cos_sin
+            qkv = torch.randn(n, (args.hq + 2 * args.hkv) * 128, device="cuda").to(torch.bfloat16)
+            qw = torch.ones(128, device="cuda", dtype=torch.bfloat16)
+            cs = build_cos_sin(128, 4096, 1e6, "cuda")
+            pos = (ctx.long() - 1)
+            slots = torch.from_numpy(a["slot_mapping"]).cuda()
+            qv = qkv[:, :args.hq * 128].view(n, args.hq, 128)
+
+            def run_two():
+                for layer in range(L):
+                    ops.qknorm_rope_store(layer, qkv, args.hq, args.hkv, pos, qw, qw, cs, 1e-6, slots)
+                    ops.paged_decode(layer, qv, bt, ctx, 0.0884, out=out)
+
+            def run_fused():
+                for layer in range(L):
+                    ops.paged_decode_fused(layer, qkv, args.hq, qw, qw, cs, 1e-6, bt, ctx, 0.0884, out=out)
+
+            row = dict(step=st, batch=n)
+            for name, fn in (("two_kernels_us", run_two), ("fused_us", run_fused)):
+                fn(); fn()
+                best = 1e9
+                for _ in range(args.reps):
+                    flush.fill_(1)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record(); fn(); e1.record()
+                    torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1) / L)
+                row[name] = round(best * 1000, 2)
+            print(json.dumps(row))
             continue
         for _ in range(2):
             for layer in range(L):
