@@ -56,5 +56,6 @@ extern "C" int b200_kv_bind(b200_ctx* ctx, void* k_base, void* v_base, int layer
     ctx->block_shift = shift;
     ctx->num_kv_heads = num_kv_heads;
     ctx->head_dim = head_dim;
+    ctx->bind_gen++;
     return B200_OK;
 }

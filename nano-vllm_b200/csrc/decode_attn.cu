@@ -21,42 +21,11 @@
 #include <cstring>
 #include <type_traits>
 
-#include "common.cuh"
+#include "decode_common.cuh"
+
+using namespace b200dec;
 
 namespace {
-
-constexpr int CHUNK = 16;                          // tokens per pipeline stage
-constexpr int ROW_BYTES = B200_HEAD_DIM * 2;       // one token of one kv head
-constexpr int CHUNK_BYTES = CHUNK * ROW_BYTES;     // 4096
-constexpr int MAX_BATCH = 1024;                    // sequences per launch (prefix table in smem)
-constexpr int MIN_CHUNKS = 8;                      // smallest range handed to one warp (128 tokens)
-
-struct DecodeParams {
-    const __nv_bfloat16* q;
-    int64_t q_stride;
-    __nv_bfloat16* out;
-    int64_t out_stride;
-    const __nv_bfloat16* k_layer;
-    const __nv_bfloat16* v_layer;
-    const int32_t* block_tables;
-    int bt_stride;
-    const int32_t* context_lens;
-    int batch;
-    int hkv;
-    int block_shift;
-    float scale_log2;
-    float* part_o;    // [slots][G][128]
-    float* part_ml;   // [slots][G][2]
-    int* counters;    // [batch * hkv], zero on entry, zero on exit
-    // fused mode (b200_paged_decode_fused): q points at the raw qkv GEMM output; the kernel itself applies
-    // q/k RMSNorm + RoPE and appends the step's K/V row to the cache
-    const __nv_bfloat16* q_norm_w;
-    const __nv_bfloat16* k_norm_w;
-    const float* cos_sin;
-    __nv_bfloat16* k_layer_w;   // writable aliases of k_layer / v_layer
-    __nv_bfloat16* v_layer_w;
-    float eps;
-};
 
 constexpr int CS_BYTES = B200_HEAD_DIM * 4;        // one cos|sin row of the rotary table
 
@@ -72,33 +41,6 @@ struct DecodeSmem {
     static constexpr int kOffP = kOffBars + NWARPS * NSTAGES * 8;       // float[NWARPS][G][16]
     static constexpr int kOffWarpTot = kOffP + NWARPS * G * 16 * 4;     // int[NWARPS]
     static constexpr int kTotal = kOffWarpTot + 32 * 4;
-};
-
-// Walks chunks in (sequence, kv head, chunk) order.  Warp-uniform.
-struct ChunkCursor {
-    int b, h, ck, n, ctx;
-    __device__ __forceinline__ void seek(const int* cum, const int* ctxs, int batch, int hkv, long long c) {
-        int key = (int)(c / hkv);
-        int lo = 0, hi = batch;            // largest b with cum[b] <= key
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (cum[mid] <= key) lo = mid; else hi = mid;
-        }
-        b = lo;
-        n = cum[b + 1] - cum[b];
-        ctx = ctxs[b];
-        int rem = (int)(c - (long long)hkv * cum[b]);
-        h = rem / n;
-        ck = rem - h * n;
-    }
-    __device__ __forceinline__ void advance(const int* cum, const int* ctxs, int batch, int hkv) {
-        if (++ck < n) return;
-        ck = 0;
-        if (++h < hkv) return;
-        h = 0;
-        do { ++b; } while (b < batch && cum[b + 1] == cum[b]);
-        if (b < batch) { n = cum[b + 1] - cum[b]; ctx = ctxs[b]; }
-    }
 };
 
 template <int G, int NWARPS, int NSTAGES, bool FUSED>
@@ -612,6 +554,17 @@ extern "C" size_t b200_decode_workspace_bytes(const b200_ctx* ctx, int max_batch
     return ws_layout(ctx->sm_count, max_batch, ctx->num_kv_heads, num_q_heads / ctx->num_kv_heads).total;
 }
 
+int b200_decode_mma_launch(b200_ctx* ctx, int layer, const DecodeParams& prm, int G, cudaStream_t stream);
+
+static bool use_mma_decode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200_DECODE");
+        v = (e && !strcmp(e, "mma")) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static int decode_common(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0, const int32_t* block_tables,
                          int bt_stride, const int32_t* context_lens, void* out, int64_t out_stride0, int batch,
                          int num_q_heads, float scale, void* workspace, size_t workspace_bytes, void* stream,
@@ -657,6 +610,7 @@ static int decode_common(b200_ctx* ctx, int layer, const void* q, int64_t q_stri
     prm.part_ml = reinterpret_cast<float*>(ws + w.off_ml);
     prm.part_o = reinterpret_cast<float*>(ws + w.off_o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!fused && use_mma_decode()) return b200_decode_mma_launch(ctx, layer, prm, G, st);
     if (fused) {
         switch (G) {
             case 1: return launch_decode<1, true>(ctx, prm, st);
