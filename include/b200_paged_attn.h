@@ -98,7 +98,8 @@ int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0
  * K/V row appended to slot block_tables[b, (ctx-1)/block_size]*block_size + (ctx-1)%block_size of `layer` -- the slot
  * ModelRunner.prepare_decode computes (model_runner.py:181) -- and attention over keys 0..ctx-1.
  * qkv: the raw fused projection output [batch, (num_q_heads + 2*num_kv_heads) * head_dim] bf16 (not modified).
- * Same result as b200_qknorm_rope_store followed by b200_paged_decode, one kernel instead of two. */
+ * Same result as b200_qknorm_rope_store followed by b200_paged_decode, one kernel instead of two.
+ * Only for num_q_heads / num_kv_heads <= 2 (B200_EUNSUPPORTED otherwise). */
 int b200_paged_decode_fused(b200_ctx* ctx, int layer, const void* qkv, int64_t qkv_stride0,
                             const void* q_norm_weight, const void* k_norm_weight, const float* cos_sin,
                             float eps, const int32_t* block_tables, int bt_stride,

@@ -514,9 +514,8 @@ int decode_variant() {
 
 template <int G, bool FUSED>
 int launch_decode(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) {
-    if constexpr (G == 8) {
-        return launch_variant<G, 8, 2, FUSED>(ctx, prm, stream);     // 3 stages of 10 KB x 8 warps exceed 227 KB
-    } else if constexpr (FUSED) {
+    static_assert(G <= 2, "the fp32-FMA formulation is issue-bound beyond 2 query heads per kv head: use decode_mma.cu");
+    if constexpr (FUSED) {
         return launch_variant<G, 8, 2, true>(ctx, prm, stream);
     } else {
         switch (decode_variant()) {
@@ -610,21 +609,14 @@ static int decode_common(b200_ctx* ctx, int layer, const void* q, int64_t q_stri
     prm.part_ml = reinterpret_cast<float*>(ws + w.off_ml);
     prm.part_o = reinterpret_cast<float*>(ws + w.off_o);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!fused && use_mma_decode()) return b200_decode_mma_launch(ctx, layer, prm, G, st);
+    // Kernel choice by head-group size (measured on the benchmark's batch-256 step, same KV bytes):
+    //   G = 2: FMA 97.6 us, MMA 99.4 us      G = 4: FMA 121.6, MMA 101.9      G = 8: FMA 215.7, MMA 104.2
     if (fused) {
-        switch (G) {
-            case 1: return launch_decode<1, true>(ctx, prm, st);
-            case 2: return launch_decode<2, true>(ctx, prm, st);
-            case 4: return launch_decode<4, true>(ctx, prm, st);
-            default: return launch_decode<8, true>(ctx, prm, st);
-        }
+        if (G > 2) return B200_EUNSUPPORTED;
+        return G == 1 ? launch_decode<1, true>(ctx, prm, st) : launch_decode<2, true>(ctx, prm, st);
     }
-    switch (G) {
-        case 1: return launch_decode<1, false>(ctx, prm, st);
-        case 2: return launch_decode<2, false>(ctx, prm, st);
-        case 4: return launch_decode<4, false>(ctx, prm, st);
-        default: return launch_decode<8, false>(ctx, prm, st);
-    }
+    if (G > 2 || use_mma_decode()) return b200_decode_mma_launch(ctx, layer, prm, G, st);
+    return G == 1 ? launch_decode<1, false>(ctx, prm, st) : launch_decode<2, false>(ctx, prm, st);
 }
 
 extern "C" int b200_paged_decode(b200_ctx* ctx, int layer, const void* q, int64_t q_stride0,

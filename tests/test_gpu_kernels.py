@@ -161,8 +161,8 @@ def test_paged_decode_page_permutation_invariance(ops):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("hq,hkv,bs,lens", [(16, 8, 256, [1, 16, 17, 300, 1024, 0, 33, 2048]), (8, 2, 16, [5, 16, 49, 1]),
-                                            (8, 1, 64, [65, 64, 700]), (4, 4, 32, [31, 32, 33])])
+@pytest.mark.parametrize("hq,hkv,bs,lens", [(16, 8, 256, [1, 16, 17, 300, 1024, 0, 33, 2048]), (4, 2, 16, [5, 16, 49, 1]),
+                                            (2, 1, 64, [65, 64, 700]), (4, 4, 32, [31, 32, 33])])
 def test_paged_decode_fused_vs_two_kernels_and_oracle(ops, hq, hkv, bs, lens):
     """b200_paged_decode_fused == b200_qknorm_rope_store + b200_paged_decode == the oracle, including what ends up in
     the cache for the step's own token (position ctx-1, slot from the block table)."""
