@@ -39,11 +39,19 @@ def main():
     torch.cuda.synchronize()
     dt = time.time() - t
     bm = llm.scheduler.block_manager
-    same = outs[0]["token_ids"] == outs[-2]["token_ids"] and outs[1]["token_ids"] == outs[-1]["token_ids"]
+    def agree(a, b):                      # leading tokens on which two runs of the same prompt agree
+        k = 0
+        while k < len(a) and a[k] == b[k]:
+            k += 1
+        return k
+    # identical prompts served in different batches (one of them through the prefix cache): with random-init
+    # weights the logits are nearly flat, so a one-ulp difference between batch shapes can flip an argmax;
+    # the agreement length is reported, not asserted
+    same = [agree(outs[0]["token_ids"], outs[-2]["token_ids"]), agree(outs[1]["token_ids"], outs[-1]["token_ids"])]
     print(json.dumps({"config": "Qwen3-8B dims random-init bf16, block_size 16, prefix cache, 1xB200", "seqs": n,
                       "max_tokens": max_tokens, "output_tok_s": n * max_tokens / dt, "seconds": dt, "init_s": init_s,
                       "kv_blocks": llm.config.num_kvcache_blocks, "cached_hashes": len(bm.hash_to_block_id),
-                      "duplicate_prompts_reproduce": bool(same)}))
+                      "duplicate_prompt_agreement_tokens": same}))
     llm.exit()
 
 
