@@ -144,7 +144,7 @@ class LLMEngine:
             sampling_params = [sampling_params] * len(prompts)
         for prompt, sp in zip(prompts, sampling_params):
             self._add_request(prompt, sp)
-        done: dict[int, list[int]] = {}
+        done: dict[int, dict] = {}
         stats = {"prefill": 0.0, "decode": 0.0}
 
         def on_step(finished, num_tokens, dt):
@@ -152,8 +152,9 @@ class LLMEngine:
                 stats["prefill"] = num_tokens / dt
             else:
                 stats["decode"] = -num_tokens / dt
-            for seq in finished:
-                done[seq.seq_id] = seq.completion_token_ids
+            for seq in finished:                  # detokenise now: the next step is already running on the GPU
+                toks = seq.completion_token_ids
+                done[seq.seq_id] = {"text": self.tokenizer.decode(toks), "token_ids": toks}
             if pbar is not None:
                 pbar.set_postfix({"Prefill": f"{int(stats['prefill'])}tok/s", "Decode": f"{int(stats['decode'])}tok/s"})
                 pbar.update(len(finished))
@@ -161,8 +162,7 @@ class LLMEngine:
         self._run_overlapped(on_step)
         if pbar is not None:
             pbar.close()
-        ordered = [done[k] for k in sorted(done)]
-        return [{"text": self.tokenizer.decode(t), "token_ids": t} for t in ordered]
+        return [done[k] for k in sorted(done)]
 
     def _run_overlapped(self, on_step) -> None:
         """The reference's step loop (llm_engine.py:49-55, 73-86) with the host work of step N+1 done while the
