@@ -68,70 +68,131 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_kernel(const __nv_bfloat
     }
 }
 
+// Same two ops, one WARP per row (no block barrier) for rows of at most 2048 elements: a decode step has only a few
+// hundred rows, so the kernel is pure latency and the shorter dependency chain wins.
+template <bool HAS_RES, int NV>   // NV = uint4 per lane, cols = NV * 256
+__global__ void __launch_bounds__(128) rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride,
+                                                           __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w,
+                                                           __nv_bfloat16* out, int64_t out_stride, int rows, float eps) {
+    constexpr int cols = NV * 256;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* x4 = reinterpret_cast<const uint4*>(x + (int64_t)row * x_stride);
+    uint4* r4 = HAS_RES ? reinterpret_cast<uint4*>(residual + (int64_t)row * cols) : nullptr;
+    const uint4* w4 = reinterpret_cast<const uint4*>(w);
+    uint4* o4 = reinterpret_cast<uint4*>(out + (int64_t)row * out_stride);
+    uint4 xin[NV], rin[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        xin[k] = x4[lane + k * 32];
+        if (HAS_RES) rin[k] = r4[lane + k * 32];
+    }
+    float v[NV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        unpack8(xin[k], v[k]);
+        if (HAS_RES) {
+            float r[8];
+            unpack8(rin[k], r);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[k][e] += r[e];
+            r4[lane + k * 32] = pack8(v[k]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(v[k][e], v[k][e], ss);
+    }
+    ss = warp_sum(ss);
+    const float rstd = 1.0f / sqrtf(ss / (float)cols + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        float wf[8], y[8];
+        unpack8(w4[lane + k * 32], wf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = __fmul_rn(__fmul_rn(v[k][e], rstd), wf[e]);
+        o4[lane + k * 32] = pack8(y);
+    }
+}
+
+template <bool HAS_RES>
+bool launch_rmsnorm_warp(const __nv_bfloat16* x, int64_t xs, __nv_bfloat16* res, const __nv_bfloat16* w, __nv_bfloat16* out,
+                         int64_t os, int rows, int cols, float eps, cudaStream_t st) {
+    if (cols % 256 || cols > 2048 || rows > 4096) return false;       // big prefill batches keep the block-per-row kernel
+    const unsigned grid = (rows + 3) / 4;
+    switch (cols / 256) {
+        case 1: rmsnorm_warp_kernel<HAS_RES, 1><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
+        case 2: rmsnorm_warp_kernel<HAS_RES, 2><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
+        case 4: rmsnorm_warp_kernel<HAS_RES, 4><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
+        case 8: rmsnorm_warp_kernel<HAS_RES, 8><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
+        default: return false;
+    }
+}
+
 // q_norm / k_norm (models/qwen3.py:82-84) + rotary_emb (layers/rotary_embedding.py:37-48) +
-// store_kvcache (layers/attention.py:10-40) over the fused qkv GEMM output.  One warp per
-// (token, head); lane l owns elements {2l, 2l+1} of each rotation half.
+// store_kvcache (layers/attention.py:10-40) over the fused qkv GEMM output.  One HALF-warp per (token, head):
+// lane j owns elements 8j..8j+7 (one 16-byte access), its rotation partner (element +-64) is lane j^8.
 __global__ void __launch_bounds__(128) qknorm_rope_store_kernel(
     __nv_bfloat16* qkv, int64_t stride, int hq, int hkv, const int64_t* __restrict__ positions,
     const __nv_bfloat16* __restrict__ qw, const __nv_bfloat16* __restrict__ kw,
     const float* __restrict__ cos_sin, float eps, const int32_t* __restrict__ slot_mapping,
     __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int block_shift, int n) {
     const int heads = hq + 2 * hkv;
-    const int64_t gwarp = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (gwarp >= (int64_t)n * heads) return;
-    const int tok = (int)(gwarp / heads);
-    const int head = (int)(gwarp - (int64_t)tok * heads);
-    const int lane = threadIdx.x & 31;
-    __nv_bfloat16* src = qkv + (int64_t)tok * stride + head * B200_HEAD_DIM;
+    const int64_t unit = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 4;        // (token, head) index
+    const int j = threadIdx.x & 15;
+    const int64_t total = (int64_t)n * heads;
+    // the shuffles below involve whole warps: a warp whose second half-warp is past the end still runs them
+    const bool live = unit < total;
+    const int64_t u = live ? unit : total - 1;
+    const int tok = (int)(u / heads);
+    const int head = (int)(u - (int64_t)tok * heads);
+    __nv_bfloat16* src = qkv + (int64_t)tok * stride + head * B200_HEAD_DIM + j * 8;
 
     int slot = -1;
     if (slot_mapping != nullptr && k_cache != nullptr) slot = slot_mapping[tok];
+    const int64_t crow = slot < 0 ? 0
+        : ((((int64_t)(slot >> block_shift)) * hkv) << block_shift) + (slot & ((1 << block_shift) - 1));   // + kvh << shift below
 
-    if (head >= hq + hkv) {                       // a value head: scatter only
-        if (slot < 0) return;
-        const int kvh = head - hq - hkv;
-        const int64_t row = ((((int64_t)(slot >> block_shift)) * hkv + kvh) << block_shift) + (slot & ((1 << block_shift) - 1));
-        reinterpret_cast<uint2*>(v_cache + row * B200_HEAD_DIM)[lane] = reinterpret_cast<const uint2*>(src)[lane];
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const bool is_v = head >= hq + hkv;
+    const bool is_q = head < hq;
+    float x[8];
+    unpack8(raw, x);
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = 1.0f / sqrtf(ss / (float)B200_HEAD_DIM + eps);
+    float wf[8];
+    unpack8(*reinterpret_cast<const uint4*>((is_q ? qw : kw) + j * 8), wf);
+    const float* cs = cos_sin + positions[tok] * B200_HEAD_DIM + (j & 7) * 8;
+    const float4 c0 = *reinterpret_cast<const float4*>(cs), c1 = *reinterpret_cast<const float4*>(cs + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(cs + 64), s1 = *reinterpret_cast<const float4*>(cs + 68);
+    const float cosv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sinv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float y[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        // the reference's norm is its own kernel: its output is a stored bf16 tensor
+        const float nv = round_bf16(__fmul_rn(__fmul_rn(x[e], rstd), wf[e]));
+        const float other = __shfl_xor_sync(0xffffffffu, nv, 8);
+        y[e] = (j < 8) ? __fsub_rn(__fmul_rn(nv, cosv[e]), __fmul_rn(other, sinv[e]))
+                       : __fadd_rn(__fmul_rn(nv, cosv[e]), __fmul_rn(other, sinv[e]));
+    }
+    if (!live) return;
+    if (is_v) {                                    // a value head: scatter only
+        if (slot >= 0) {
+            const int kvh = head - hq - hkv;
+            *reinterpret_cast<uint4*>(v_cache + (crow + ((int64_t)kvh << block_shift)) * B200_HEAD_DIM + j * 8) = raw;
+        }
         return;
     }
-
-    const bool is_q = head < hq;
-    const uint32_t a = reinterpret_cast<const uint32_t*>(src)[lane];         // x1: elements 2l, 2l+1
-    const uint32_t b = reinterpret_cast<const uint32_t*>(src + 64)[lane];    // x2: 64+2l, 64+2l+1
-    float x1[2] = {bf16lo(a), bf16hi(a)};
-    float x2[2] = {bf16lo(b), bf16hi(b)};
-    float ss = x1[0] * x1[0];
-    ss = fmaf(x1[1], x1[1], ss);
-    ss = fmaf(x2[0], x2[0], ss);
-    ss = fmaf(x2[1], x2[1], ss);
-    ss = warp_sum(ss);
-    const float rstd = 1.0f / sqrtf(ss / (float)B200_HEAD_DIM + eps);
-    const __nv_bfloat16* w = is_q ? qw : kw;
-    const uint32_t wa = reinterpret_cast<const uint32_t*>(w)[lane];
-    const uint32_t wb = reinterpret_cast<const uint32_t*>(w + 64)[lane];
-    // the reference's norm is its own kernel: its output is a stored bf16 tensor
-    x1[0] = round_bf16(__fmul_rn(__fmul_rn(x1[0], rstd), bf16lo(wa)));
-    x1[1] = round_bf16(__fmul_rn(__fmul_rn(x1[1], rstd), bf16hi(wa)));
-    x2[0] = round_bf16(__fmul_rn(__fmul_rn(x2[0], rstd), bf16lo(wb)));
-    x2[1] = round_bf16(__fmul_rn(__fmul_rn(x2[1], rstd), bf16hi(wb)));
-
-    const float* cs = cos_sin + positions[tok] * B200_HEAD_DIM;
-    const float2 c = reinterpret_cast<const float2*>(cs)[lane];
-    const float2 s = reinterpret_cast<const float2*>(cs + 64)[lane];
-    const float y1a = __fsub_rn(__fmul_rn(x1[0], c.x), __fmul_rn(x2[0], s.x));
-    const float y1b = __fsub_rn(__fmul_rn(x1[1], c.y), __fmul_rn(x2[1], s.y));
-    const float y2a = __fadd_rn(__fmul_rn(x2[0], c.x), __fmul_rn(x1[0], s.x));
-    const float y2b = __fadd_rn(__fmul_rn(x2[1], c.y), __fmul_rn(x1[1], s.y));
-    const uint32_t o1 = pack_bf16x2(y1a, y1b);
-    const uint32_t o2 = pack_bf16x2(y2a, y2b);
-    reinterpret_cast<uint32_t*>(src)[lane] = o1;
-    reinterpret_cast<uint32_t*>(src + 64)[lane] = o2;
+    const uint4 outv = pack8(y);
+    *reinterpret_cast<uint4*>(src) = outv;
     if (!is_q && slot >= 0) {
         const int kvh = head - hq;
-        const int64_t row = ((((int64_t)(slot >> block_shift)) * hkv + kvh) << block_shift) + (slot & ((1 << block_shift) - 1));
-        __nv_bfloat16* dst = k_cache + row * B200_HEAD_DIM;
-        reinterpret_cast<uint32_t*>(dst)[lane] = o1;
-        reinterpret_cast<uint32_t*>(dst + 64)[lane] = o2;
+        *reinterpret_cast<uint4*>(k_cache + (crow + ((int64_t)kvh << block_shift)) * B200_HEAD_DIM + j * 8) = outv;
     }
 }
 
@@ -199,6 +260,9 @@ extern "C" int b200_rmsnorm(const void* x, int64_t x_stride0, const void* weight
     if (cols <= 0 || cols % 8 || cols > NORM_THREADS * NORM_MAXV * 8) return B200_EUNSUPPORTED;
     if (x_stride0 % 8 || out_stride0 % 8 || !aligned16(x) || !aligned16(out) || !aligned16(weight)) return B200_EINVAL;
     if (rows == 0) return B200_OK;
+    if (launch_rmsnorm_warp<false>(static_cast<const __nv_bfloat16*>(x), x_stride0, nullptr, static_cast<const __nv_bfloat16*>(weight),
+                                   static_cast<__nv_bfloat16*>(out), out_stride0, rows, cols, eps, static_cast<cudaStream_t>(stream)))
+        return b200_launch_status(nullptr);
     rmsnorm_kernel<false><<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), x_stride0, nullptr, static_cast<const __nv_bfloat16*>(weight),
         static_cast<__nv_bfloat16*>(out), out_stride0, cols, eps);
@@ -211,6 +275,10 @@ extern "C" int b200_add_rmsnorm(const void* x, void* residual, const void* weigh
     if (cols <= 0 || cols % 8 || cols > NORM_THREADS * NORM_MAXV * 8) return B200_EUNSUPPORTED;
     if (!aligned16(x) || !aligned16(out) || !aligned16(weight) || !aligned16(residual)) return B200_EINVAL;
     if (rows == 0) return B200_OK;
+    if (launch_rmsnorm_warp<true>(static_cast<const __nv_bfloat16*>(x), cols, static_cast<__nv_bfloat16*>(residual),
+                                  static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, rows, cols, eps,
+                                  static_cast<cudaStream_t>(stream)))
+        return b200_launch_status(nullptr);
     rmsnorm_kernel<true><<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), cols, static_cast<__nv_bfloat16*>(residual),
         static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, cols, eps);
@@ -233,8 +301,8 @@ extern "C" int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64
         vc = ctx->v_layer(layer);
         shift = ctx->block_shift;
     }
-    const int64_t warps = (int64_t)n * (num_q_heads + 2 * num_kv_heads);
-    const unsigned blocks = (unsigned)((warps + 3) / 4);
+    const int64_t units = (int64_t)n * (num_q_heads + 2 * num_kv_heads);       // one half-warp each, 8 per block
+    const unsigned blocks = (unsigned)((units + 7) / 8);
     qknorm_rope_store_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<__nv_bfloat16*>(qkv), qkv_stride0, num_q_heads, num_kv_heads, positions,
         static_cast<const __nv_bfloat16*>(q_norm_weight), static_cast<const __nv_bfloat16*>(k_norm_weight),

@@ -6,7 +6,7 @@ inside them.  Per layer and per step this issues
 
     add_rmsnorm -> qkv GEMM -> [q/k-norm + RoPE + KV scatter] -> paged attention -> o GEMM (+all-reduce)
     -> add_rmsnorm -> gate_up GEMM -> silu*mul -> down GEMM (+all-reduce)
-(b200_paged_decode_fused can run the bracket and the decode attention as one kernel; see fused_decode below)
+(for small decode batches the bracket and the attention are one kernel, b200_paged_decode_fused)
 
 GEMMs are library calls (cuBLAS through ``F.linear``, as in the reference, linear.py:51,73,153);
 everything else is one hand-written kernel from libb200attn.  Tensor parallelism shards heads and
@@ -67,10 +67,11 @@ class Qwen3ForCausalLM:
         self.q_size = self.num_heads * self.head_dim
         self.kv_size = self.num_kv_heads * self.head_dim
         self.tie = bool(getattr(c, "tie_word_embeddings", False))
-        # b200_paged_decode_fused folds q/k-norm + RoPE + KV append into the decode kernel.  Measured on the
-        # benchmark shapes it saves 1-2 us per layer below batch ~128 and loses 2 us at batch 256 (the extra
-        # per-segment math lands on the already issue-bound warps), so the two-kernel path stays the default.
-        self.fused_decode = False
+        # b200_paged_decode_fused folds q/k-norm + RoPE + KV append into the decode kernel (one launch less per
+        # layer).  Measured on the benchmark shapes it saves 1-2 us per layer up to batch ~128 and loses 2 us at
+        # batch 256 (the extra per-segment math lands on warps that are already busy), so it is used for decode
+        # batches up to this many rows; it exists for head groups <= 2 only.
+        self.fused_decode_max_batch = 128 if self.num_heads // self.num_kv_heads <= 2 else 0
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
         theta = getattr(c, "rope_theta", 1000000.0)
@@ -161,7 +162,7 @@ class Qwen3ForCausalLM:
             qkv = F.linear(x, L.qkv)
             cached = attn.k_cache.numel() > 0
             t = qkv.shape[0]
-            if cached and not ctx.is_prefill and self.fused_decode:
+            if cached and not ctx.is_prefill and t <= self.fused_decode_max_batch:
                 # decode: q/k-norm, RoPE, KV append and attention in ONE launch on the raw projection output
                 o = ops.paged_decode_fused(li, qkv, hq, L.q_norm, L.k_norm, self.cos_sin, eps, ctx.block_tables,
                                            ctx.context_lens, attn.scale)
