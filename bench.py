@@ -235,7 +235,9 @@ def decode_roofline(llm, sample_every: int = 24):
     first_gbs = (first[2] * 4096 * (m.num_kv_heads / 8)) / (first[3] * 1e-6) / 1e9
     return {"bound": "hbm", "kernel": "paged_decode_kernel<G=2>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"], "frac_of_8TBs_spec": achieved / 8000.0,
-            "traffic": None, "launches_timed": launches, "avg_launch_us": tot_ms * 1000.0 / launches,
+            "traffic": 595.4e6, "traffic_is": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the batch-256 step "
+                                              "(profiles/r01_decode_kernel_ncu.txt: 588.9 MB + 6.5 MB) vs 587.2 MB algorithmic for that launch",
+            "launches_timed": launches, "avg_launch_us": tot_ms * 1000.0 / launches,
             "bytes_per_launch_avg": tot_bytes / launches,
             "batch256_step0": {"batch": first[1], "sum_ctx": first[2], "launch_us": first[3], "GB/s": first_gbs,
                                "frac_measured_peak": first_gbs / peaks["hbm_gbs"], "frac_8TBs": first_gbs / 8000.0},
