@@ -95,6 +95,9 @@ class ModelRunner:
         self.model = Qwen3ForCausalLM(hf, rank, self.world_size, self.device, max_position=hf.max_position_embeddings)
         load_model(self.model, config.model, allow_random=bool(os.environ.get("NANOVLLM_ALLOW_RANDOM_INIT")))
         self.vocab_offset = rank * self.model.vocab_shard
+        if self.world_size > 1:
+            from .peer_reduce import PeerReduce
+            self.model.peer = PeerReduce.create(min(config.max_num_seqs, 1024), hf.hidden_size, rank, self.world_size, self.device)
 
         if config.max_num_seqs > 1024:
             raise ValueError("max_num_seqs > 1024 is not supported by the decode kernel's per-launch batch table")

@@ -72,6 +72,7 @@ class Qwen3ForCausalLM:
         # batch 256 (the extra per-segment math lands on warps that are already busy), so it is used for decode
         # batches up to this many rows; it exists for head groups <= 2 only.
         self.fused_decode_max_batch = 128 if self.num_heads // self.num_kv_heads <= 2 else 0
+        self.peer = None        # engine/peer_reduce.PeerReduce when tensor parallel over NVLink peer memory
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
         theta = getattr(c, "rope_theta", 1000000.0)
@@ -142,23 +143,35 @@ class Qwen3ForCausalLM:
         return iter(self.attn)
 
     # ---- forward -------------------------------------------------------------------------------
-    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+    def _row_linear(self, x: torch.Tensor, w: torch.Tensor):
+        """Row-parallel GEMM (o_proj / down_proj).  Returns (partial, in_peer_buffer)."""
+        peer = self.peer
+        if peer is not None and x.shape[0] <= peer.rows_cap:
+            out = peer.next_out(x.shape[0])
+            torch.mm(x, w.t(), out=out)
+            return out, True
+        return F.linear(x, w), False
+
+    def _reduce_add_norm(self, h, in_peer: bool, residual, weight):
+        """all-reduce over the TP ranks + residual add + RMSNorm (linear.py:152-156 + layernorm.py:28-40)."""
+        if in_peer:
+            return self.peer.reduce_add_norm(h.shape[0], residual, weight, self.eps)
         if self.tp_size > 1:
-            dist.all_reduce(t)
-        return t
+            dist.all_reduce(h)
+        return ops.add_rmsnorm(h, residual, weight, self.eps)
 
     @torch.inference_mode()
     def forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         ctx = get_context()
         eps, hq, hkv, d = self.eps, self.num_heads, self.num_kv_heads, self.head_dim
         h = ops.embedding(input_ids, self.embed)
-        residual = None
+        residual, in_peer = None, False
         for li, L in enumerate(self.layers):
             attn = self.attn[li]
             if residual is None:
                 residual, x = h, ops.rmsnorm(h, L.ln1, eps)
             else:
-                x, residual = ops.add_rmsnorm(h, residual, L.ln1, eps)
+                x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln1)
             qkv = F.linear(x, L.qkv)
             cached = attn.k_cache.numel() > 0
             t = qkv.shape[0]
@@ -173,10 +186,10 @@ class Qwen3ForCausalLM:
                 k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
                 v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
                 o = attn(q, k, v, kv_stored=True)
-            h = self._all_reduce(F.linear(o.reshape(t, self.q_size), L.o))
-            x, residual = ops.add_rmsnorm(h, residual, L.ln2, eps)
-            h = self._all_reduce(F.linear(ops.silu_mul(F.linear(x, L.gate_up)), L.down))
-        x, _ = ops.add_rmsnorm(h, residual, self.norm, eps)
+            h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o)
+            x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln2)
+            h, in_peer = self._row_linear(ops.silu_mul(F.linear(x, L.gate_up)), L.down)
+        x, _ = self._reduce_add_norm(h, in_peer, residual, self.norm)
         return x
 
     __call__ = forward
