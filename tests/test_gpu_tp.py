@@ -20,3 +20,11 @@ def test_tp2_engine_matches_oracle(eager):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "TP_RESULT" in r.stdout and '"ok": true' in r.stdout
+
+
+def test_tp2_spawned_by_the_engine():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tp_spawn_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SPAWN_RESULT" in r.stdout and '"ok": true' in r.stdout
