@@ -399,3 +399,71 @@ def test_errors_are_loud(ops):
     with pytest.raises(B200Error):
         ops.rmsnorm(torch.zeros(2, 16, device="cuda"), torch.ones(16, device="cuda"), 1e-6)   # fp32
     assert math.isfinite(1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the operator seam: Attention module + Context, used the way the reference's model uses it
+# ---------------------------------------------------------------------------------------------
+def test_attention_module_seam_vs_oracle(ops):
+    """Attention(num_heads, head_dim, scale, num_kv_heads).forward(q, k, v) reading the global Context and doing its own
+    store_kvcache (reference layers/attention.py:59-75), for a packed prefill, a paged prefill and a decode step."""
+    from types import SimpleNamespace
+    from nanovllm.layers.attention import Attention
+    from nanovllm.layers.activation import SiluAndMul
+    from nanovllm.layers.layernorm import RMSNorm
+    from nanovllm.layers.sampler import Sampler
+    from nanovllm.utils.context import reset_context, set_context
+    from oracle.paged_attention_ref import attention_forward_ref
+    hq, hkv, bs, nblk = 4, 2, 16, 12
+    kv, ks, vs = bind_random_cache(ops, 1, nblk, hkv, bs, seed=81)
+    attn = Attention(hq, 128, 128 ** -0.5, hkv)
+    attn.k_cache, attn.v_cache, attn.layer_id = kv[0, 0], kv[1, 0], 0
+    lens = [20, 7]
+    tables = make_tables([40, 30], bs, nblk, seed=3)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32)
+
+    def both(q, k, v, ctx_cpu):
+        want = attention_forward_ref(q, k, v, ks[0], vs[0], ctx_cpu, 128 ** -0.5, p_dtype=torch.bfloat16 if ctx_cpu.is_prefill else None)
+        g = lambda t: None if t is None else t.cuda()
+        set_context(ctx_cpu.is_prefill, g(ctx_cpu.cu_seqlens_q), g(ctx_cpu.cu_seqlens_k), ctx_cpu.max_seqlen_q, ctx_cpu.max_seqlen_k,
+                    g(ctx_cpu.slot_mapping), g(ctx_cpu.context_lens), g(ctx_cpu.block_tables))
+        got = attn(q.cuda(), k.cuda(), v.cuda())
+        reset_context()
+        return got.reshape(want.shape), want
+
+    # 1. packed prefill of two prompts
+    tot = sum(lens)
+    q, k, v = bf(tot, hq, 128, seed=1), bf(tot, hkv, 128, seed=2), bf(tot, hkv, 128, seed=3)
+    slots = [int(tables[s, p // bs]) * bs + p % bs for s, n in enumerate(lens) for p in range(n)]
+    c = SimpleNamespace(is_prefill=True, cu_seqlens_q=i32([0, 20, 27]), cu_seqlens_k=i32([0, 20, 27]), max_seqlen_q=20, max_seqlen_k=20,
+                        slot_mapping=i32(slots), context_lens=None, block_tables=None)
+    got, want = both(q, k, v, c)
+    assert_close_bf16(got, want, "Attention module: packed prefill")
+    assert torch.equal(to_logical(kv[0, 0].cpu()), ks[0]) and torch.equal(to_logical(kv[1, 0].cpu()), vs[0])
+    # 2. second chunk of the first prompt through the paged path (len_q 5 over 25 keys)
+    q, k, v = bf(5, hq, 128, seed=4), bf(5, hkv, 128, seed=5), bf(5, hkv, 128, seed=6)
+    slots = [int(tables[0, p // bs]) * bs + p % bs for p in range(20, 25)]
+    c = SimpleNamespace(is_prefill=True, cu_seqlens_q=i32([0, 5]), cu_seqlens_k=i32([0, 25]), max_seqlen_q=5, max_seqlen_k=25,
+                        slot_mapping=i32(slots), context_lens=None, block_tables=tables[:1])
+    got, want = both(q, k, v, c)
+    assert_close_bf16(got, want, "Attention module: paged prefill")
+    # 3. decode of both sequences
+    q, k, v = bf(2, hq, 128, seed=7), bf(2, hkv, 128, seed=8), bf(2, hkv, 128, seed=9)
+    ctxl = [26, 8]
+    slots = [int(tables[s, (n - 1) // bs]) * bs + (n - 1) % bs for s, n in enumerate(ctxl)]
+    c = SimpleNamespace(is_prefill=False, cu_seqlens_q=None, cu_seqlens_k=None, max_seqlen_q=0, max_seqlen_k=0,
+                        slot_mapping=i32(slots), context_lens=i32(ctxl), block_tables=tables)
+    got, want = both(q, k, v, c)
+    assert got.shape == want.shape
+    assert_close_bf16(got, want, "Attention module: decode")
+    assert torch.equal(to_logical(kv[0, 0].cpu()), ks[0])
+    # the other drop-in modules
+    x = bf(9, 512, seed=10)
+    norm = RMSNorm(512).cuda().to(torch.bfloat16)
+    assert_close_bf16(norm(x.cuda()), rmsnorm_ref(x, norm.weight.cpu(), 1e-6), "RMSNorm module", ulps=1.01)
+    y, r = norm(x.cuda(), x.cuda().clone())
+    wy, wr = add_rmsnorm_ref(x, x, norm.weight.cpu(), 1e-6)
+    assert torch.equal(r.cpu(), wr)
+    assert_close_bf16(SiluAndMul()(x.cuda()), silu_mul_ref(x), "SiluAndMul module", ulps=1.01)
+    lg = bf(5, 4096, seed=11)
+    assert torch.equal(Sampler()(lg.cuda(), torch.zeros(5).cuda()).cpu(), lg.float().argmax(-1))
