@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
     // block-table load never sits on the issue path
     int pg_next = 0;
     if (lane == 0) pg_next = p.block_tables[(int64_t)pi.b * p.bt_stride + ((pi.ck * CHUNK) >> p.block_shift)];
+    const uint64_t l2pol = l2_policy_evict_first();
 
     auto issue = [&](int i) {                             // chunk i of this warp's range
         if (lane == 0) {
@@ -164,8 +165,13 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
             const bool seg_first = (pi.ck == 0) || (i == 0);      // the consumer starts a segment on this chunk
             mbar_expect_tx(bar, 2 * bytes + (seg_first ? (uint32_t)(L::kQBytes + (FUSED ? CS_BYTES : 0)) : 0u));
             if (bytes) {
-                bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
-                bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
+                if (p.l2_hint) {
+                    bulk_g2s_hint(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar, l2pol);
+                    bulk_g2s_hint(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar, l2pol);
+                } else {
+                    bulk_g2s(dst, p.k_layer + row * B200_HEAD_DIM, bytes, bar);
+                    bulk_g2s(dst + CHUNK_BYTES, p.v_layer + row * B200_HEAD_DIM, bytes, bar);
+                }
             }
             if (seg_first) {
                 bulk_g2s(dst + 2 * CHUNK_BYTES, p.q + (int64_t)pi.b * p.q_stride + pi.h * G * B200_HEAD_DIM, L::kQBytes, bar);
@@ -604,6 +610,12 @@ static int decode_common(b200_ctx* ctx, int layer, const void* q, int64_t q_stri
     prm.k_norm_w = static_cast<const __nv_bfloat16*>(k_norm_w);
     prm.cos_sin = cos_sin;
     prm.eps = eps;
+    {
+        static int hint = -1;
+        // measured on the benchmark's decode steps: 97.8 -> 96.1 us at batch 256, 91.2 -> 90.0 at 126, 46.0 -> 45.0 at 37
+        if (hint < 0) { const char* e = getenv("B200_DECODE_L2HINT"); hint = (e && e[0] == '0') ? 0 : 1; }
+        prm.l2_hint = hint;
+    }
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     prm.counters = reinterpret_cast<int*>(ws);
     prm.part_ml = reinterpret_cast<float*>(ws + w.off_ml);

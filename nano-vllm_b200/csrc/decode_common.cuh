@@ -36,6 +36,7 @@ struct DecodeParams {
     __nv_bfloat16* k_layer_w;   // writable aliases of k_layer / v_layer
     __nv_bfloat16* v_layer_w;
     float eps;
+    int l2_hint;                // 1: K/V bulk copies carry an L2 evict_first policy (tuning knob)
 };
 
 // Walks chunks in (sequence, kv head, chunk) order.  Warp-uniform.

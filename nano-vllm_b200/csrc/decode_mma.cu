@@ -36,10 +36,11 @@ struct MmaSmem {
     static constexpr int kTotal = kOffWarpTot + 32 * 4;
 };
 
-__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row) {
+// K/V are streamed exactly once per launch: the boxes carry an L2 evict_first policy
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int col, int row, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-            "r"(dst), "l"(map), "r"(bar), "r"(col), "r"(row)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(col), "r"(row), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -156,6 +157,7 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
 
     int pg_next = 0;
     if (lane == 0) pg_next = p.block_tables[(int64_t)pi.b * p.bt_stride + ((pi.ck * CHUNK) >> p.block_shift)];
+    const uint64_t l2pol = l2_policy_evict_first();
 
     auto issue = [&](int i) {
         if (lane == 0) {
@@ -166,10 +168,10 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
             const uint32_t dst = my_stages_u32 + slot * L::kStageBytes;
             const bool seg_first = (pi.ck == 0) || (i == 0);
             mbar_expect_tx(bar, KV_STAGE + (seg_first ? (uint32_t)L::kQBytes : 0u));
-            tma_box(dst, &tm_k, bar, 0, (int)row);
-            tma_box(dst + HALF_BYTES, &tm_k, bar, 64, (int)row);
-            tma_box(dst + 2 * HALF_BYTES, &tm_v, bar, 0, (int)row);
-            tma_box(dst + 3 * HALF_BYTES, &tm_v, bar, 64, (int)row);
+            tma_box(dst, &tm_k, bar, 0, (int)row, l2pol);
+            tma_box(dst + HALF_BYTES, &tm_k, bar, 64, (int)row, l2pol);
+            tma_box(dst + 2 * HALF_BYTES, &tm_v, bar, 0, (int)row, l2pol);
+            tma_box(dst + 3 * HALF_BYTES, &tm_v, bar, 64, (int)row, l2pol);
             if (seg_first)
                 bulk_g2s(dst + KV_STAGE, p.q + (int64_t)pi.b * p.q_stride + pi.h * G * B200_HEAD_DIM, L::kQBytes, bar);
         }
