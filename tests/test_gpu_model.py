@@ -64,7 +64,19 @@ def test_model_script_vs_oracle(preset):
             assert margin <= tol, f"step {i} row {r}: greedy token {tok} loses by {margin} in the oracle (tol {tol})"
             flips += tok != int(w[r].argmax())
             rows += 1
-    record("model_script", dict(preset=preset, worst_rel_l2=worst_rel, greedy_rows=rows, greedy_differ=flips))
+    # and directly against the committed golden vectors: the logits the REFERENCE's own nn.Modules produced on CPU
+    # (tests/golden/model_*.npz, eager rounding) -- same script, same weights
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"model_{preset}.npz"))
+    worst_gold = 0.0
+    for i, g in enumerate(got):
+        w = torch.from_numpy(gold[f"logits_{i}"]).view(torch.bfloat16).float()
+        rel = ((g - w).norm() / w.norm()).item()
+        worst_gold = max(worst_gold, rel)
+        assert rel < 2.5e-2, f"step {i}: logits vs the reference modules' golden output: relative L2 {rel}"
+    record("model_script", dict(preset=preset, worst_rel_l2=worst_rel, worst_rel_l2_vs_reference_golden=worst_gold,
+                                greedy_rows=rows, greedy_differ=flips))
 
 
 @pytest.fixture(scope="module")
