@@ -467,51 +467,3 @@ def test_attention_module_seam_vs_oracle(ops):
     assert_close_bf16(SiluAndMul()(x.cuda()), silu_mul_ref(x), "SiluAndMul module", ulps=1.01)
     lg = bf(5, 4096, seed=11)
     assert torch.equal(Sampler()(lg.cuda(), torch.zeros(5).cuda()).cpu(), lg.float().argmax(-1))
-
-
-# ---------------------------------------------------------------------------------------------
-# tensor-parallel exchange kernel: the 8-participant protocol, emulated on ONE GPU
-# ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("world", [2, 8])
-def test_allreduce_add_rmsnorm_protocol_single_gpu(world):
-    """b200_allreduce_add_rmsnorm with `world` participants living on one device: one stream per emulated rank, every
-    rank's slice in ordinary device memory.  Checks the epoch handshake over several rounds (alternating buffers), that
-    all ranks produce identical bits, and the arithmetic against the oracle's add_rmsnorm of the summed partials."""
-    from nanovllm import _native as nat
-    lib = nat.load()
-    rows, cols, eps = 24, 1024, 1e-6
-    buf_bytes = rows * cols * 2
-    flag_off = 2 * buf_bytes
-    slab = torch.zeros(world, flag_off + 256, dtype=torch.uint8, device="cuda")
-    bases = torch.tensor([slab[r].data_ptr() for r in range(world)], dtype=torch.int64, device="cuda")
-    state = torch.zeros(world, 2, dtype=torch.int32, device="cuda")
-    w = (1 + 0.1 * torch.randn(cols)).to(torch.bfloat16)
-    wg = w.cuda()
-    res_cpu = bf(rows, cols, seed=5)
-    residual = [res_cpu.cuda().clone() for _ in range(world)]
-    outs = [torch.empty(rows, cols, dtype=torch.bfloat16, device="cuda") for _ in range(world)]
-    streams = [torch.cuda.Stream() for _ in range(world)]
-    for rnd in range(4):
-        turn = rnd & 1
-        parts = [bf(rows, cols, seed=100 * rnd + r, scale=0.5) for r in range(world)]
-        for r in range(world):
-            slab[r, turn * buf_bytes:turn * buf_bytes + buf_bytes].copy_(parts[r].cuda().view(torch.uint8).view(-1))
-        torch.cuda.synchronize()
-        for r in range(world):
-            with torch.cuda.stream(streams[r]):
-                nat.check(lib.b200_allreduce_add_rmsnorm(bases.data_ptr(), turn * buf_bytes, flag_off, state[r].data_ptr(),
-                                                         state[r].data_ptr() + 4, r, world, residual[r].data_ptr(), wg.data_ptr(),
-                                                         outs[r].data_ptr(), rows, cols, eps, streams[r].cuda_stream))
-        torch.cuda.synchronize()
-        total = res_cpu.float()
-        for pt in parts:                                   # fp32 sum in rank order, as the kernel does
-            total = total + pt.float()
-        want_res = total.to(torch.bfloat16)
-        var = total.pow(2).mean(-1, keepdim=True)
-        want_out = (total * torch.rsqrt(var + eps) * w.float()).to(torch.bfloat16)
-        for r in range(world):
-            assert torch.equal(residual[r], residual[0]) and torch.equal(outs[r], outs[0]), "ranks must agree bit for bit"
-        assert torch.equal(residual[0].cpu(), want_res), f"round {rnd}: residual update"
-        assert_close_bf16(outs[0], want_out, f"round {rnd}: normalised output", ulps=1.01)
-        assert state[:, 0].tolist() == [rnd + 1] * world and state[:, 1].tolist() == [0] * world
-        res_cpu = want_res
