@@ -152,12 +152,15 @@ int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64_t qkv_stri
  * kernel over NVLink peer memory.  Every rank has written its partial GEMM output [rows, cols] bf16 at byte offset
  * data_offset of its slice of a symmetric (peer-mapped) allocation; peer_bases_dev is a DEVICE array of `world`
  * pointers to the slices' bases (e.g. torch symmetric memory's buffer_ptrs_dev); int32 flags[world] live at
- * flag_offset of every slice (zeroed once); epoch / done are two private zero-initialised device words.  Computes, on
- * every rank, bit-identically:  residual <- bf16(residual + sum_p partial_p);  out = norm(that fp32 sum) * weight.
+ * flag_offset of every slice (zeroed once); epoch / done are two private zero-initialised device words; *err_flag
+ * (device int, may be NULL) is set to 1 if a peer did not announce itself within ~2 s (the launch then completes with
+ * undefined output instead of spinning forever).  Computes, on every rank, bit-identically:
+ *   residual <- bf16(residual + sum_p partial_p);  out = norm(that fp32 sum) * weight.
  * Callers alternate two data offsets between consecutive calls (see csrc/tp_allreduce.cu for the protocol). */
 int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t data_offset, uint64_t flag_offset,
-                               int* epoch, unsigned int* done, int rank, int world, void* residual,
-                               const void* weight, void* out, int rows, int cols, float eps, void* stream);
+                               int* epoch, unsigned int* done, int* err_flag, int rank, int world,
+                               void* residual, const void* weight, void* out, int rows, int cols, float eps,
+                               void* stream);
 
 /* SiluAndMul.forward (layers/activation.py:8-11): out[r, c] = silu(x[r, c]) * x[r, inter + c]. */
 int b200_silu_mul(const void* x, void* out, int rows, int inter, void* stream);

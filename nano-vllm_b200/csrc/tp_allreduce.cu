@@ -32,8 +32,8 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 }
 
 __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
-    void* const* __restrict__ bases, uint64_t data_off, uint64_t flag_off, int* epoch, unsigned int* done, int rank, int world,
-    __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* out, int cols, float eps) {
+    void* const* __restrict__ bases, uint64_t data_off, uint64_t flag_off, int* epoch, unsigned int* done, int* err, int rank,
+    int world, __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* out, int cols, float eps) {
     __shared__ float red[4];
     __shared__ int s_epoch;
     const int row = blockIdx.x;
@@ -46,9 +46,17 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
                 if (p != rank) st_release_sys(reinterpret_cast<int*>(static_cast<uint8_t*>(bases[p]) + flag_off) + rank, e + 1);
         }
         const int* mine = reinterpret_cast<const int*>(static_cast<const uint8_t*>(bases[rank]) + flag_off);
+        // A peer that never shows up (a rank died, a mis-wired handle) must not wedge the GPU: after ~2 s of
+        // waiting the launch gives up, raises *err and lets the host fall back to NCCL (engine/peer_reduce.py).
+        const long long t0 = clock64();
         for (int p = 0; p < world; ++p)
             if (p != rank)
-                while (ld_acquire_sys(mine + p) - (e + 1) < 0) {}
+                while (ld_acquire_sys(mine + p) - (e + 1) < 0) {
+                    if (clock64() - t0 > (1ll << 32)) {
+                        if (err) atomicExch(err, 1);
+                        break;
+                    }
+                }
     }
     __syncthreads();
 
@@ -110,14 +118,15 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
 }  // namespace
 
 extern "C" int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t data_offset, uint64_t flag_offset,
-                                          int* epoch, unsigned int* done, int rank, int world, void* residual,
-                                          const void* weight, void* out, int rows, int cols, float eps, void* stream) {
+                                          int* epoch, unsigned int* done, int* err_flag, int rank, int world,
+                                          void* residual, const void* weight, void* out, int rows, int cols, float eps,
+                                          void* stream) {
     if (!peer_bases_dev || !epoch || !done || !residual || !weight || !out || rows < 0) return B200_EINVAL;
     if (world < 2 || world > AR_MAX_WORLD || rank < 0 || rank >= world) return B200_EINVAL;
     if (cols <= 0 || cols % 8 || cols > AR_THREADS * AR_MAXV * 8 || (data_offset & 15) || (flag_offset & 3)) return B200_EUNSUPPORTED;
     if (rows == 0) return B200_OK;
     allreduce_add_rmsnorm_kernel<<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<void* const*>(peer_bases_dev), data_offset, flag_offset, epoch, done, rank, world,
+        static_cast<void* const*>(peer_bases_dev), data_offset, flag_offset, epoch, done, err_flag, rank, world,
         static_cast<__nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, eps);
     return b200_launch_status(nullptr);
 }

@@ -31,24 +31,62 @@ class PeerReduce:
         torch.cuda.synchronize()
         self.handle = symm.rendezvous(self.raw, dist.group.WORLD)
         self.bases_dev = int(self.handle.buffer_ptrs_dev)
-        self.state = torch.zeros(2, dtype=torch.int32, device=device)           # [epoch, done counter]
+        self.state = torch.zeros(3, dtype=torch.int32, device=device)           # [epoch, done counter, error flag]
         self.views = [self.raw[i * self.buf_bytes:i * self.buf_bytes + rows_cap * hidden * 2].view(torch.bfloat16).view(rows_cap, hidden)
                       for i in range(2)]
         self.turn = 0
         self.calls = 0
-        torch.cuda.synchronize()
-        dist.barrier()
+        torch.cuda.synchronize()                      # the caller's agreement all-reduce is the cross-rank barrier
+
+    @staticmethod
+    def _all_agree(ok: bool, device) -> bool:
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # also a barrier
+        return int(flag.item()) == 1
 
     @classmethod
     def create(cls, rows_cap, hidden, rank, world, device):
+        """The workspace, or None -- decided unanimously -- when peer memory cannot be set up or fails its self-test."""
         if os.environ.get("B200_TP_ALLREDUCE", "peer") != "peer":
             return None
+        obj, why = None, ""
         try:
-            return cls(rows_cap, hidden, rank, world, device)
-        except Exception as e:                       # no P2P / fabric handles on this box: NCCL stays in charge
+            obj = cls(rows_cap, hidden, rank, world, device)
+        except Exception as e:                       # no P2P / fabric handles on this box, ...
+            why = f"{type(e).__name__}: {e}"
+        if not cls._all_agree(obj is not None, device):          # some rank could not map its peers: nobody uses it
             if rank == 0:
-                print(f"[nanovllm] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+                print(f"[nanovllm] peer-memory all-reduce unavailable ({why or 'set-up failed on another rank'}); using NCCL", flush=True)
             return None
+        try:
+            ok = obj.self_test()
+        except Exception as e:
+            ok, why = False, f"{type(e).__name__}: {e}"
+        if not cls._all_agree(ok, device):
+            if rank == 0:
+                print(f"[nanovllm] peer-memory all-reduce failed its self-test ({why or 'mismatch or timeout'}); using NCCL", flush=True)
+            return None
+        return obj
+
+    def self_test(self, rounds: int = 4, rows: int = 8) -> bool:
+        """A few real exchanges checked against an NCCL all-reduce of the same data; also trips the kernel's
+        wait timeout (error flag) instead of hanging if a peer is unreachable."""
+        gen = torch.Generator(device="cpu").manual_seed(1234 + self.rank)
+        weight = torch.ones(self.hidden, dtype=torch.bfloat16, device=self.raw.device)
+        good = True
+        for _ in range(rounds):
+            part = torch.randn(rows, self.hidden, generator=gen).to(torch.bfloat16).to(self.raw.device)
+            self.next_out(rows).copy_(part)
+            residual = torch.zeros(rows, self.hidden, dtype=torch.bfloat16, device=self.raw.device)
+            _, got = self.reduce_add_norm(rows, residual, weight, 1e-6)
+            want = part.float()
+            dist.all_reduce(want)
+            torch.cuda.synchronize()
+            # never leave the loop early: every rank must issue the same collectives whatever it observes
+            timed_out = int(self.state[2].item()) != 0
+            err = (got.float() - want).abs().max().item()
+            good = good and not timed_out and err <= 2.0 ** -7 * max(want.abs().max().item(), 1.0)   # one bf16 rounding
+        return good
 
     def next_out(self, rows: int) -> torch.Tensor:
         """Where the row-parallel GEMM of the next exchange must write its partial (the two buffers alternate)."""
@@ -61,8 +99,8 @@ class PeerReduce:
             out = torch.empty_like(residual)
         lib = nat.load()
         nat.check(lib.b200_allreduce_add_rmsnorm(self.bases_dev, self.turn * self.buf_bytes, self.flag_off,
-                                                 self.state.data_ptr(), self.state.data_ptr() + 4, self.rank, self.world,
-                                                 residual.data_ptr(), weight.data_ptr(), out.data_ptr(), rows, self.hidden, eps,
-                                                 ops._stream()))
+                                                 self.state.data_ptr(), self.state.data_ptr() + 4, self.state.data_ptr() + 8,
+                                                 self.rank, self.world, residual.data_ptr(), weight.data_ptr(), out.data_ptr(),
+                                                 rows, self.hidden, eps, ops._stream()))
         self.calls += 1
         return out, residual
