@@ -153,7 +153,7 @@ int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64_t qkv_stri
  * data_offset of its slice of a symmetric (peer-mapped) allocation; peer_bases_dev is a DEVICE array of `world`
  * pointers to the slices' bases (e.g. torch symmetric memory's buffer_ptrs_dev); int32 flags[world] live at
  * flag_offset of every slice (zeroed once); epoch / done are two private zero-initialised device words; *err_flag
- * (device int, may be NULL) is set to 1 if a peer did not announce itself within ~2 s (the launch then completes with
+ * (device int, may be NULL) is set to 1 if a peer did not announce itself within ~18 s (the launch then completes with
  * undefined output instead of spinning forever).  Computes, on every rank, bit-identically:
  *   residual <- bf16(residual + sum_p partial_p);  out = norm(that fp32 sum) * weight.
  * Callers alternate two data offsets between consecutive calls (see csrc/tp_allreduce.cu for the protocol). */

@@ -46,13 +46,14 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
                 if (p != rank) st_release_sys(reinterpret_cast<int*>(static_cast<uint8_t*>(bases[p]) + flag_off) + rank, e + 1);
         }
         const int* mine = reinterpret_cast<const int*>(static_cast<const uint8_t*>(bases[rank]) + flag_off);
-        // A peer that never shows up (a rank died, a mis-wired handle) must not wedge the GPU: after ~2 s of
-        // waiting the launch gives up, raises *err and lets the host fall back to NCCL (engine/peer_reduce.py).
+        // A peer that never shows up (a rank died, a mis-wired handle) must not wedge the GPU: after 2^35 cycles
+        // (~18 s, far beyond any skew between lock-stepped ranks) the launch gives up and raises *err; the
+        // start-up self-test (engine/peer_reduce.py) then switches every rank to NCCL.
         const long long t0 = clock64();
         for (int p = 0; p < world; ++p)
             if (p != rank)
                 while (ld_acquire_sys(mine + p) - (e + 1) < 0) {
-                    if (clock64() - t0 > (1ll << 32)) {
+                    if (clock64() - t0 > (1ll << 35)) {
                         if (err) atomicExch(err, 1);
                         break;
                     }
