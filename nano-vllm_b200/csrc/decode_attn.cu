@@ -17,6 +17,11 @@
 //   * a kv-head's context that straddles several warps leaves (m, l, O) partials in a small
 //     workspace; the last warp to arrive (per-pair counter) merges them in fixed order, so the
 //     result is deterministic and no second launch is needed.
+//
+// This file holds the fp32-FMA formulation, used for head groups G <= 2 (Qwen3-0.6B), where it reads HBM at
+// 6.1 TB/s (93 % of the measured copy peak).  decode_mma.cu is the warp-level tensor-core formulation of the same
+// schedule for G >= 4.  The FUSED template flag (b200_paged_decode_fused) makes the kernel take the raw qkv
+// projection and do q/k-norm, RoPE and the KV append itself.  K/V bulk copies carry an L2 evict_first policy.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>

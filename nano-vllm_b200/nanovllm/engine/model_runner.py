@@ -6,8 +6,11 @@ is_prefill) -> list[int]`` returns one token id per sequence; one process per GP
 everything on the current stream, one device->host sync per step.
 
 B200-first differences (DESIGN.md "runner"):
-* per-step metadata travels in ONE pinned staging buffer and ONE host->device copy into static
-  device buffers (the reference builds seven pinned tensors and seven copies per step);
+* per-step metadata travels in ONE pinned staging buffer (two of them, ping-pong, so step N+1 can be staged
+  while step N runs) and ONE host->device copy into static device buffers (the reference builds seven pinned
+  tensors and seven copies per step);
+* launch() / collect() split a step into "enqueue everything" and "wait for its tokens"; up to two steps are in
+  flight, a decode step's input ids are gathered on the device from the previous step's samples;
 * the decode graph contains the whole step: embedding ... final norm, LM head, sampling and (under
   tensor parallelism) the all-reduces; the reference leaves logits and sampling outside;
 * tensor-parallel ranks are SPMD replicas: every rank runs the same (deterministic) scheduler and
