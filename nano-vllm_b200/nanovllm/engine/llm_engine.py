@@ -162,6 +162,7 @@ class LLMEngine:
         self._run_overlapped(on_step)
         if pbar is not None:
             pbar.close()
+        self.model_runner.check_peer_exchange()
         return [done[k] for k in sorted(done)]
 
     def _run_overlapped(self, on_step) -> None:

@@ -116,6 +116,12 @@ class ModelRunner:
         if not self.enforce_eager:
             self.capture_cudagraph()
 
+    def check_peer_exchange(self) -> None:
+        """Raise if the fused NVLink all-reduce hit its wait timeout since the last check (peer_reduce.py)."""
+        peer = getattr(self.model, "peer", None)
+        if peer is not None:
+            peer.raise_if_timed_out()
+
     # ---- measurement hooks (bench.py) ----------------------------------------------------------
     def begin_profile(self):
         """Record a CUDA-event pair around every step's GPU work until end_profile()."""

@@ -88,6 +88,13 @@ class PeerReduce:
             good = good and not timed_out and err <= 2.0 ** -7 * max(want.abs().max().item(), 1.0)   # one bf16 rounding
         return good
 
+    def raise_if_timed_out(self) -> None:
+        """The kernel gives up (error flag, undefined output) rather than spin forever when a peer never announces
+        its epoch; callers check after each batch of work so that such a run fails loudly instead of returning junk."""
+        if int(self.state[2].item()) != 0:
+            raise RuntimeError("tensor-parallel peer exchange timed out (a rank stopped or fell >10 s behind); "
+                               "results of this call are invalid -- rerun with B200_TP_ALLREDUCE=nccl to bypass")
+
     def next_out(self, rows: int) -> torch.Tensor:
         """Where the row-parallel GEMM of the next exchange must write its partial (the two buffers alternate)."""
         self.turn ^= 1
