@@ -194,6 +194,28 @@ int b200_sample(const void* logits, int logits_is_fp32, int64_t logits_stride0,
                 uint64_t seed, uint64_t step, const int64_t* step_dev, int64_t* out,
                 int64_t* out_keys, void* stream);
 
+/* ---- staged for the next round: compiled and exported, NOT yet run on a GPU, not on the product path -------------
+ * (tests are opt-in: B200_EXPERIMENTAL=1 pytest tests/test_gpu_linear.py -m gpu)
+ *
+ * F.linear of the reference's *ParallelLinear layers (layers/linear.py:51,73,153) for small batches, on tcgen05,
+ * with what follows fused in (csrc/linear_tc.cu):
+ *   x [rows, k] bf16 (row stride x_stride0), w [n, k] bf16 contiguous, k % 64 == 0.
+ *   epilogue 0: out[rows, n_out] bf16 = bf16(x w^T)                                      (k_splits must be 1)
+ *   epilogue 1: w is [2 * n_out, k] (gate rows then up rows, the reference's gate_up_proj);
+ *               out[rows, n_out] = SiluAndMul(bf16(x w^T))  (layers/activation.py:8-11)  (k_splits must be 1)
+ *   epilogue 2: out is fp32 [k_splits, rows, n_out] (out_stride0 = n_out): per-split partial sums, to be
+ *               consumed in order by b200_add_rmsnorm_partials
+ * block_n: accumulator columns per CTA, one of 16 (not for epilogue 1), 32, 64, 128; n_out must be a multiple of
+ * block_n (block_n / 2 for epilogue 1).  flags bit 0: launch with programmatic stream serialization (the kernel
+ * prefetches its weight tiles before waiting for the previous kernel in the stream). */
+int b200_linear(const void* x, int64_t x_stride0, const void* w, void* out, int64_t out_stride0, int rows,
+                int n_out, int k, int epilogue, int block_n, int k_splits, int flags, void* stream);
+
+/* RMSNorm.add_rms_forward (layers/layernorm.py:28-40) whose input is a split-K projection:
+ *   h = bf16(sum_s partials[s]) in split order (deterministic), then as b200_add_rmsnorm.  cols <= 8192. */
+int b200_add_rmsnorm_partials(const float* partials, int splits, void* residual, const void* weight, void* out,
+                              int rows, int cols, float eps, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,41 @@ def sample(logits: torch.Tensor, temperatures: torch.Tensor | None, seed: int, s
 def tokens_from_keys(keys: torch.Tensor) -> torch.Tensor:
     """Decode the token ids out of (all-reduced) sample keys."""
     return 0xffffffff - (keys & 0xffffffff)
+
+
+# ---- staged for the next round (csrc/linear_tc.cu): not yet run on a GPU, not used by the engine ---------------------
+EPI_BF16, EPI_SILU, EPI_PARTIAL = 0, 1, 2
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, block_n: int = 32, k_splits: int = 1,
+           pdl: bool = False, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x [rows, k] @ w[n, k]^T on tcgen05.  EPI_SILU: w = [gate; up] rows, returns silu(gate) * up [rows, n/2];
+    EPI_PARTIAL: returns fp32 [k_splits, rows, n] partial sums for ``add_rmsnorm_partials``."""
+    _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.shape[1] == w.shape[1]
+    rows, k = x.shape
+    n_out = w.shape[0] // 2 if epilogue == EPI_SILU else w.shape[0]
+    if out is None:
+        if epilogue == EPI_PARTIAL:
+            out = torch.empty(k_splits, rows, n_out, dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty(rows, n_out, dtype=torch.bfloat16, device=x.device)
+    lib = nat.load()
+    nat.check(lib.b200_linear(x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(-2), rows, n_out, k,
+                              epilogue, block_n, k_splits, int(pdl), _stream()))
+    return out
+
+
+def add_rmsnorm_partials(partials: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float,
+                         pdl: bool = False, out: torch.Tensor | None = None):
+    """residual <- bf16(bf16(sum_s partials[s]) + residual); returns (rmsnorm(residual) * weight, residual)."""
+    _need(partials, torch.float32, "partials"); _need(residual, torch.bfloat16, "residual"); _need(weight, torch.bfloat16, "weight")
+    assert partials.dim() == 3 and partials.is_contiguous() and residual.is_contiguous()
+    splits, rows, cols = partials.shape
+    assert residual.shape == (rows, cols)
+    if out is None:
+        out = torch.empty_like(residual)
+    lib = nat.load()
+    nat.check(lib.b200_add_rmsnorm_partials(partials.data_ptr(), splits, residual.data_ptr(), weight.data_ptr(), out.data_ptr(),
+                                            rows, cols, eps, int(pdl), _stream()))
+    return out, residual

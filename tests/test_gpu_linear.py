@@ -1,0 +1,124 @@
+"""Opt-in parity tests for the staged tcgen05 linear layer (csrc/linear_tc.cu).
+
+The kernel was written after this round's GPU budget was spent and has never run; an untested tensor-core kernel can
+hang as well as be wrong, so these tests only run when asked for:
+
+    B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_linear.py -m gpu -x -q
+
+Reference for every case: torch fp32 matmul of the same bf16 inputs, rounded where the reference rounds
+(F.linear output is bf16, layers/linear.py:51,73,153; SiluAndMul in fp32 on that, layers/activation.py:8-11).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1",
+                                 reason="staged kernel, never run on a GPU: set B200_EXPERIMENTAL=1 to try it")]
+
+
+def _inputs(rows, n, k, seed=0, x_pad=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xb = torch.randn(rows, k + x_pad, generator=g).to(torch.bfloat16).cuda()
+    x = xb[:, :k]
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(torch.bfloat16).cuda()
+    return x, w
+
+
+@pytest.mark.parametrize("rows", [1, 37, 128, 129, 256])
+@pytest.mark.parametrize("n,k,block_n", [(4096, 1024, 32), (4096, 1024, 64), (1024, 2048, 16), (1024, 3072, 128), (512, 64, 32)])
+def test_linear_bf16(rows, n, k, block_n):
+    from nanovllm import ops
+    x, w = _inputs(rows, n, k, seed=rows + n)
+    got = ops.linear(x, w, ops.EPI_BF16, block_n)
+    torch.cuda.synchronize()
+    want = (x.float() @ w.float().t())
+    err = (got.float() - want).abs().max().item()
+    # fp32 accumulation in a different order + one bf16 rounding of the output
+    assert err <= 2.0 ** -7 * want.abs().max().item() + 1e-3, err
+
+
+def test_linear_strided_x():
+    from nanovllm import ops
+    x, w = _inputs(100, 1024, 1024, seed=5, x_pad=64)       # row stride 1088: a view into a wider buffer
+    got = ops.linear(x, w, ops.EPI_BF16, 32)
+    want = x.float() @ w.float().t()
+    assert (got.float() - want).abs().max().item() <= 2.0 ** -7 * want.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("rows", [1, 64, 200, 256])
+@pytest.mark.parametrize("block_n", [32, 64, 128])
+def test_linear_silu(rows, block_n):
+    from nanovllm import ops
+    inter, k = 3072, 1024
+    x, w = _inputs(rows, 2 * inter, k, seed=rows)
+    got = ops.linear(x, w, ops.EPI_SILU, block_n)
+    y = (x.float() @ w.float().t()).to(torch.bfloat16).float()
+    g, u = y[:, :inter], y[:, inter:]
+    want = (g * torch.sigmoid(g) * u)
+    err = (got.float() - want).abs().max().item()
+    assert err <= 2.0 ** -6 * want.abs().max().item() + 1e-3, err
+    # and against the two-kernel path it replaces, which shares the rounding points exactly up to accumulation order
+    two = ops.silu_mul((x @ w.t()).contiguous())
+    assert (got.float() - two.float()).abs().max().item() <= 2.0 ** -6 * want.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("rows", [1, 130, 256])
+@pytest.mark.parametrize("k,splits,block_n", [(2048, 4, 64), (3072, 8, 64), (3072, 6, 32), (1024, 1, 16)])
+def test_linear_splitk_add_rmsnorm(rows, k, splits, block_n):
+    from nanovllm import ops
+    n = 1024
+    x, w = _inputs(rows, n, k, seed=rows + k)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    residual = torch.randn(rows, n, generator=g).to(torch.bfloat16).cuda()
+    weight = (1 + 0.1 * torch.randn(n, generator=g)).to(torch.bfloat16).cuda()
+    parts = ops.linear(x, w, ops.EPI_PARTIAL, block_n, splits)
+    assert parts.shape == (splits, rows, n)
+    want_h = x.float() @ w.float().t()
+    assert (parts.sum(0) - want_h).abs().max().item() <= 1e-3 * max(1.0, want_h.abs().max().item())
+    res_a, res_b = residual.clone(), residual.clone()
+    out_a, _ = ops.add_rmsnorm_partials(parts, res_a, weight, 1e-6)
+    h = parts[0].clone()
+    for s in range(1, splits):
+        h += parts[s]
+    out_b, _ = ops.add_rmsnorm(h.to(torch.bfloat16), res_b, weight, 1e-6)
+    assert torch.equal(res_a, res_b)                                         # same rounding points, same order
+    # the normalised rows may differ by one rounding: the two kernels add the squares in a different order
+    assert (out_a.float() - out_b.float()).abs().max().item() <= 2.0 ** -7 * out_b.float().abs().max().item()
+    # run-to-run determinism
+    parts2 = ops.linear(x, w, ops.EPI_PARTIAL, block_n, splits)
+    assert torch.equal(parts, parts2)
+
+
+def test_linear_pdl_chain_in_graph():
+    """Programmatic dependent launch: a chain of our kernels captured in a CUDA graph gives the eager result."""
+    from nanovllm import ops
+    rows, hidden, inter = 64, 1024, 3072
+    x, w1 = _inputs(rows, 2 * inter, hidden, seed=1)
+    _, w2 = _inputs(rows, hidden, inter, seed=2)
+    g0 = torch.Generator(device="cpu").manual_seed(3)
+    residual0 = torch.randn(rows, hidden, generator=g0).to(torch.bfloat16).cuda()
+    weight = torch.ones(hidden, dtype=torch.bfloat16, device="cuda")
+
+    def chain(pdl, residual):
+        a = ops.linear(x, w1, ops.EPI_SILU, 32, pdl=pdl)
+        p = ops.linear(a, w2, ops.EPI_PARTIAL, 64, 8, pdl=pdl)
+        return ops.add_rmsnorm_partials(p, residual, weight, 1e-6, pdl=pdl)[0]
+
+    want = chain(False, residual0.clone())
+    torch.cuda.synchronize()
+    res = residual0.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        chain(True, res.clone())                      # warm-up outside capture (cudaFuncSetAttribute, map cache)
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    static_res = residual0.clone()
+    with torch.cuda.graph(graph):
+        got = chain(True, static_res)
+    for _ in range(3):
+        static_res.copy_(residual0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
