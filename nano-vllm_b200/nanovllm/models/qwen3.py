@@ -19,6 +19,7 @@ list of launches, which is what gets captured into the decode CUDA graphs.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -73,6 +74,12 @@ class Qwen3ForCausalLM:
         # batches up to this many rows; it exists for head groups <= 2 only.
         self.fused_decode_max_batch = 128 if self.num_heads // self.num_kv_heads <= 2 else 0
         self.peer = None        # engine/peer_reduce.PeerReduce when tensor parallel over NVLink peer memory
+        # Staged for the next round and OFF by default: B200_LINEAR=tc routes the decode-size projections through
+        # csrc/linear_tc.cu (tcgen05, SiluAndMul / split-K add+RMSNorm fused) instead of cuBLAS.  That kernel has not
+        # run on a GPU yet.  B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
+        self.tc_linear = os.environ.get("B200_LINEAR", "cublas") == "tc" and tp_size == 1
+        self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "32,32,64,8,64,8,0").split(",")]
+        self.tc_max_rows = 256
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
         theta = getattr(c, "rope_theta", 1000000.0)
@@ -143,8 +150,11 @@ class Qwen3ForCausalLM:
         return iter(self.attn)
 
     # ---- forward -------------------------------------------------------------------------------
-    def _row_linear(self, x: torch.Tensor, w: torch.Tensor):
-        """Row-parallel GEMM (o_proj / down_proj).  Returns (partial, in_peer_buffer)."""
+    def _row_linear(self, x: torch.Tensor, w: torch.Tensor, tc=None):
+        """Row-parallel GEMM (o_proj / down_proj).  Returns (partial, where): where is True when the partial sits in
+        the peer-mapped buffer, "parts" when it is the fp32 split-K partials of the staged tcgen05 path."""
+        if tc is not None:
+            return ops.linear(x, w, ops.EPI_PARTIAL, tc[0], tc[1], pdl=bool(self.tc_cfg[6])), "parts"
         peer = self.peer
         if peer is not None and x.shape[0] <= peer.rows_cap:
             out = peer.next_out(x.shape[0])
@@ -154,6 +164,8 @@ class Qwen3ForCausalLM:
 
     def _reduce_add_norm(self, h, in_peer: bool, residual, weight):
         """all-reduce over the TP ranks + residual add + RMSNorm (linear.py:152-156 + layernorm.py:28-40)."""
+        if in_peer == "parts":
+            return ops.add_rmsnorm_partials(h, residual, weight, self.eps, pdl=bool(self.tc_cfg[6]))
         if in_peer:
             return self.peer.reduce_add_norm(h.shape[0], residual, weight, self.eps)
         if self.tp_size > 1:
@@ -166,13 +178,15 @@ class Qwen3ForCausalLM:
         eps, hq, hkv, d = self.eps, self.num_heads, self.num_kv_heads, self.head_dim
         h = ops.embedding(input_ids, self.embed)
         residual, in_peer = None, False
+        cfg = self.tc_cfg
+        tc = self.tc_linear and h.shape[0] <= self.tc_max_rows
         for li, L in enumerate(self.layers):
             attn = self.attn[li]
             if residual is None:
                 residual, x = h, ops.rmsnorm(h, L.ln1, eps)
             else:
                 x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln1)
-            qkv = F.linear(x, L.qkv)
+            qkv = ops.linear(x, L.qkv, ops.EPI_BF16, cfg[0], pdl=bool(cfg[6])) if tc else F.linear(x, L.qkv)
             cached = attn.k_cache.numel() > 0
             t = qkv.shape[0]
             if cached and not ctx.is_prefill and t <= self.fused_decode_max_batch:
@@ -186,9 +200,13 @@ class Qwen3ForCausalLM:
                 k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
                 v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
                 o = attn(q, k, v, kv_stored=True)
-            h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o)
+            h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o, (cfg[2], cfg[3]) if tc else None)
             x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln2)
-            h, in_peer = self._row_linear(ops.silu_mul(F.linear(x, L.gate_up)), L.down)
+            if tc:
+                act = ops.linear(x, L.gate_up, ops.EPI_SILU, cfg[1], pdl=bool(cfg[6]))
+            else:
+                act = ops.silu_mul(F.linear(x, L.gate_up))
+            h, in_peer = self._row_linear(act, L.down, (cfg[4], cfg[5]) if tc else None)
         x, _ = self._reduce_add_norm(h, in_peer, residual, self.norm)
         return x
 

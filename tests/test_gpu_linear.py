@@ -122,3 +122,34 @@ def test_linear_pdl_chain_in_graph():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
+def test_model_with_tc_linear_matches_library_path(preset, monkeypatch):
+    """B200_LINEAR=tc (every decode-size projection through linear_tc.cu) against the default cuBLAS path on the
+    7-step teacher-forced script: same rounding points, so only accumulation order differs."""
+    from oracle.model_script import make_script, run_script
+    from nanovllm.utils.context import reset_context, set_context
+    from nanovllm.utils.synthetic import PRESETS, random_weights
+    from test_gpu_model import build_product_model
+    weights = random_weights(PRESETS[preset], seed=1234)
+    script = make_script(PRESETS[preset]["vocab_size"])
+
+    def run(mode):
+        monkeypatch.setenv("B200_LINEAR", mode)
+        monkeypatch.setenv("B200_LINEAR_CFG", "32,32,64,4,64,4,0")
+        model, _ = build_product_model(preset, weights, script["num_blocks"], script["block_size"])
+        assert model.tc_linear == (mode == "tc")
+
+        def step(ids, pos, c):
+            set_context(c["is_prefill"], c.get("cu_seqlens_q"), c.get("cu_seqlens_k"), c.get("max_seqlen_q", 0),
+                        c.get("max_seqlen_k", 0), c.get("slot_mapping"), c.get("context_lens"), c.get("block_tables"))
+            out = model.compute_logits(model(ids, pos)).float().cpu()
+            reset_context()
+            return out
+        return run_script(torch, script, step, device="cuda")
+
+    want, got = run("cublas"), run("tc")
+    for i, (g, w) in enumerate(zip(got, want)):
+        rel = ((g - w).norm() / w.norm()).item()
+        assert rel < 1e-2, f"step {i}: relative L2 {rel}"
