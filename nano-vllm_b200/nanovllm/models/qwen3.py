@@ -73,6 +73,8 @@ class Qwen3ForCausalLM:
         # batch 256 (the extra per-segment math lands on warps that are already busy), so it is used for decode
         # batches up to this many rows; it exists for head groups <= 2 only.
         self.fused_decode_max_batch = 128 if self.num_heads // self.num_kv_heads <= 2 else 0
+        if "B200_FUSED_DECODE_MAX" in os.environ and self.fused_decode_max_batch:      # tuning knob (e.g. under TP)
+            self.fused_decode_max_batch = int(os.environ["B200_FUSED_DECODE_MAX"])
         self.peer = None        # engine/peer_reduce.PeerReduce when tensor parallel over NVLink peer memory
         # Staged for the next round and OFF by default: B200_LINEAR=tc routes the decode-size projections through
         # csrc/linear_tc.cu (tcgen05, SiluAndMul / split-K add+RMSNorm fused) instead of cuBLAS.  That kernel has not
