@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU call of the next round: validate what could not be run this round, in order of risk.
+#   gpurun --timeout 2400 -- 'bash profiles/next_round_first_call.sh'
+# Every leg has its own timeout so that a hanging staged kernel cannot take the box with it.
+mkdir -p gpurun_out
+# 1. changes made after the last validated GPU run: golden-logit comparison, peer-exchange timeout / self-test plumbing
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/nr_gpu_tests.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/nr_gpu_tests.log
+# 2. the staged tcgen05 linear layer: parity first, then the sweep, then the whole model through it
+B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_linear.py -m gpu -x -q > gpurun_out/nr_linear_tests.log 2>&1
+rc=$?; echo "linear tests rc=$rc" >> gpurun_out/nr_linear_tests.log
+if [ $rc -eq 0 ]; then
+  timeout 900 python profiles/linear_microbench.py > gpurun_out/nr_linear_microbench.json 2> gpurun_out/nr_linear_microbench.err
+  B200_LINEAR=tc timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_tc.json 2> gpurun_out/nr_bench_tc.err
+fi
+timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_default.json 2> gpurun_out/nr_bench_default.err
