@@ -71,6 +71,20 @@ def workloads() -> dict:
     s5 = [(0.8, rnd.randint(16, 200), False) for _ in range(50)]
     out["eos64"] = dict(cfg=dict(max_num_seqs=16, max_num_batched_tokens=2048, kvcache_block_size=64,
                                  num_kvcache_blocks=60), prompts=p5, sps=s5, vocab=41, eos=7)
+    # BASELINE config 4's request mix at the bookkeeping level: 1024 requests against 512 running slots, so prefill
+    # and decode steps interleave for the whole run; the cache is sized to force preemptions
+    r6 = random.Random(4)
+    p6 = [[r6.randint(0, 150000) for _ in range(r6.randint(50, 800))] for _ in range(1024)]
+    s6 = [(0.7, r6.randint(10, 200), True) for _ in range(1024)]
+    out["mixed1024"] = dict(cfg=dict(max_num_seqs=512, max_num_batched_tokens=16384, kvcache_block_size=256,
+                                     num_kvcache_blocks=1100), prompts=p6, sps=s6, vocab=151936, eos=-1)
+    # BASELINE config 5's: 128 concurrent long-context requests (about 8k in, up to 1k out); every prompt is
+    # longer than half the token budget, so prefill is chunked throughout, and blocks run out during decode
+    r7 = random.Random(5)
+    p7 = [[r7.randint(0, 150000) for _ in range(r7.randint(7000, 8192))] for _ in range(128)]
+    s7 = [(0.7, r7.randint(300, 1024), True) for _ in range(128)]
+    out["longctx128"] = dict(cfg=dict(max_num_seqs=128, max_num_batched_tokens=16384, kvcache_block_size=256,
+                                      num_kvcache_blocks=4000), prompts=p7, sps=s7, vocab=151936, eos=-1)
     return out
 
 
@@ -158,12 +172,14 @@ def reference_meta_builder(torch, block_size):
     return build
 
 
-def gen_traces(torch):
+def gen_traces(torch, only=None):
     import itertools
     from nanovllm.engine.scheduler import Scheduler
     from nanovllm.engine.sequence import Sequence
     from nanovllm.sampling_params import SamplingParams
     for name, w in workloads().items():
+        if only and name not in only:
+            continue
         cfg = types.SimpleNamespace(eos=w["eos"], **w["cfg"])
         Sequence.block_size = cfg.kvcache_block_size
         Sequence.counter = itertools.count()
@@ -259,6 +275,10 @@ def main():
     os.environ.setdefault("TORCH_COMPILE_DISABLE", "1")
     os.makedirs(GOLD, exist_ok=True)
     torch = import_reference()
+    only = sys.argv[1:]                      # e.g. `make_golden.py mixed1024 longctx128` regenerates just those traces
+    if only:
+        gen_traces(torch, only)
+        return
     gen_hash_kat()
     gen_traces(torch)
     for preset in ("tiny", "tiny-g4"):

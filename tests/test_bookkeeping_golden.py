@@ -35,7 +35,7 @@ def product_meta_builder(block_size):
     return build
 
 
-@pytest.mark.parametrize("name", ["prefix16", "chunked32", "eos64", "bench", "bench_tight"])
+@pytest.mark.parametrize("name", ["prefix16", "chunked32", "eos64", "bench", "bench_tight", "mixed1024", "longctx128"])
 def test_trace_matches_reference(name, golden_dir):
     gold = json.load(open(os.path.join(golden_dir, f"trace_{name}.json")))
     w = workloads()[name]

@@ -54,7 +54,7 @@ class FakeRunner:
         return self.queue.pop(0)
 
 
-@pytest.mark.parametrize("name", ["prefix16", "chunked32", "eos64", "bench_tight"])
+@pytest.mark.parametrize("name", ["prefix16", "chunked32", "eos64", "bench_tight", "mixed1024", "longctx128"])
 def test_overlapped_loop_equals_reference_trace(name, golden_dir):
     from nanovllm.engine.llm_engine import LLMEngine
     from nanovllm.engine.scheduler import Scheduler
