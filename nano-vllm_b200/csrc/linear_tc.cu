@@ -37,11 +37,13 @@ constexpr uint32_t X_TILE = LM * 128;     // 16 KB
 
 enum { EPI_BF16 = 0, EPI_SILU = 1, EPI_PARTIAL = 2 };
 
-template <int BN>
+// DEEP: as many ring slots as one CTA per SM allows (all of a short K in flight).  !DEEP: 4 slots for block_n <= 64, so
+// that two CTAs fit an SM and a dependent kernel launched early (PDL) finds room to prefetch its weights.
+template <int BN, bool DEEP>
 struct Cfg {
     static constexpr uint32_t W_TILE = BN * 128;
     static constexpr uint32_t STAGE = X_TILE + W_TILE;
-    static constexpr int STAGES = BN <= 32 ? 8 : (BN <= 64 ? 6 : 4);
+    static constexpr int STAGES = !DEEP ? (BN <= 64 ? 4 : 3) : (BN <= 32 ? 8 : (BN <= 64 ? 6 : 4));
     static constexpr uint32_t OFF_BAR = STAGES * STAGE;
     static constexpr uint32_t SMEM = OFF_BAR + 256;          // full[S], empty[S], done, TMEM slot
     static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -89,10 +91,10 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&acc)[BN]) {
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DEEP>
 __global__ void __launch_bounds__(L_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LinParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, DEEP>;
     constexpr int S = C::STAGES;
     constexpr uint32_t IDESC = make_idesc(LM, BN, false);
     constexpr int BOUT = EPI == EPI_SILU ? BN / 2 : BN;       // output columns of this CTA
@@ -288,12 +290,12 @@ bool cached_map(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows
     return true;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DEEP>
 int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, DEEP>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return B200_ECUDA;
+        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return B200_ECUDA;
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -306,19 +308,23 @@ int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams&
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, linear_tc_kernel<BN, EPI>, tx, tw, prm) != cudaSuccess) return B200_ECUDA;
+    if (cudaLaunchKernelEx(&cfg, linear_tc_kernel<BN, EPI, DEEP>, tx, tw, prm) != cudaSuccess) return B200_ECUDA;
     return B200_OK;
 }
 
-template <int EPI>
+template <int EPI, bool DEEP>
 int dispatch_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
     switch (bn) {
-        case 16: if constexpr (EPI == EPI_SILU) return B200_EUNSUPPORTED; else return launch_linear<16, EPI>(tx, tw, prm, grid, pdl, stream);
-        case 32: return launch_linear<32, EPI>(tx, tw, prm, grid, pdl, stream);
-        case 64: return launch_linear<64, EPI>(tx, tw, prm, grid, pdl, stream);
-        case 128: return launch_linear<128, EPI>(tx, tw, prm, grid, pdl, stream);
+        case 16: if constexpr (EPI == EPI_SILU) return B200_EUNSUPPORTED; else return launch_linear<16, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
+        case 32: return launch_linear<32, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
+        case 64: return launch_linear<64, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
+        case 128: return launch_linear<128, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
         default: return B200_EUNSUPPORTED;
     }
+}
+template <int EPI>
+int dispatch_depth(bool deep, int bn, const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
+    return deep ? dispatch_bn<EPI, true>(bn, tx, tw, prm, grid, pdl, stream) : dispatch_bn<EPI, false>(bn, tx, tw, prm, grid, pdl, stream);
 }
 
 }  // namespace
@@ -348,11 +354,12 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     dim3 grid(n_out / bout, (rows + LM - 1) / LM, k_splits);
     if (grid.y > 65535 || grid.z > 65535) return B200_EUNSUPPORTED;
     const bool pdl = (flags & 1) != 0;
+    const bool deep = (flags & 2) == 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    if (epilogue == EPI_BF16) rc = dispatch_bn<EPI_BF16>(block_n, tx, tw, prm, grid, pdl, st);
-    else if (epilogue == EPI_SILU) rc = dispatch_bn<EPI_SILU>(block_n, tx, tw, prm, grid, pdl, st);
-    else rc = dispatch_bn<EPI_PARTIAL>(block_n, tx, tw, prm, grid, pdl, st);
+    if (epilogue == EPI_BF16) rc = dispatch_depth<EPI_BF16>(deep, block_n, tx, tw, prm, grid, pdl, st);
+    else if (epilogue == EPI_SILU) rc = dispatch_depth<EPI_SILU>(deep, block_n, tx, tw, prm, grid, pdl, st);
+    else rc = dispatch_depth<EPI_PARTIAL>(deep, block_n, tx, tw, prm, grid, pdl, st);
     if (rc != B200_OK) return rc;
     return b200_launch_status(nullptr);
 }

@@ -54,8 +54,9 @@ for M in (256, 128, 64, 16, 1):
     resid = rnd(M, HID); wn = torch.ones(HID, dtype=torch.bfloat16, device="cuda")
 
     r["qkv_cublas"] = timed(lambda i: F.linear(x_h, w_qkv[i]))
-    for bn, pdl in itertools.product((16, 32, 64), (False, True)):
-        r[f"qkv_tc_bn{bn}{'_pdl' if pdl else ''}"] = timed(lambda i: ops.linear(x_h, w_qkv[i], ops.EPI_BF16, bn, pdl=pdl))
+    for bn, pdl, sh in itertools.product((16, 32, 64), (False, True), (False, True)):
+        r[f"qkv_tc_bn{bn}{'_pdl' if pdl else ''}{'_shallow' if sh else ''}"] = timed(
+            lambda i: ops.linear(x_h, w_qkv[i], ops.EPI_BF16, bn, pdl=pdl, shallow=sh))
 
     r["gate_up+silu_cublas"] = timed(lambda i: ops.silu_mul(F.linear(x_h, w_gu[i])))
     for bn, pdl in itertools.product((32, 64), (False, True)):

@@ -39,6 +39,16 @@ def test_linear_bf16(rows, n, k, block_n):
     assert err <= 2.0 ** -7 * want.abs().max().item() + 1e-3, err
 
 
+@pytest.mark.parametrize("block_n", [16, 32, 64, 128])
+def test_linear_shallow_ring(block_n):
+    from nanovllm import ops
+    x, w = _inputs(200, 1024, 2048, seed=block_n)                 # 32 k tiles through a 3-4 slot ring: many wrap-arounds
+    got = ops.linear(x, w, ops.EPI_BF16, block_n, shallow=True)
+    want = x.float() @ w.float().t()
+    assert (got.float() - want).abs().max().item() <= 2.0 ** -7 * want.abs().max().item() + 1e-3
+    assert torch.equal(got, ops.linear(x, w, ops.EPI_BF16, block_n))      # ring depth does not change the arithmetic
+
+
 def test_linear_strided_x():
     from nanovllm import ops
     x, w = _inputs(100, 1024, 1024, seed=5, x_pad=64)       # row stride 1088: a view into a wider buffer
