@@ -63,6 +63,31 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
             "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// x tile shared by the CL CTAs of a cluster (neighbouring column blocks, same rows of x): each CTA fetches 128 / CL rows
+// and multicasts them into the same ring slot of every CTA of the cluster; each copy signals the mbarrier at the same
+// offset in its destination CTA.  Cuts the L2 -> SM traffic of x, the bound of these kernels at batch >= 128, by CL.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of the mask (a ring slot is free again only
+// when all CTAs that receive multicast data in it have consumed it)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -91,10 +116,12 @@ __device__ __forceinline__ void load_acc_row(uint32_t taddr, float (&acc)[BN]) {
     }
 }
 
-template <int BN, int EPI, bool DEEP>
+template <int BN, int EPI, bool DEEP, int CL>
 __global__ void __launch_bounds__(L_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LinParams p) {
     using C = Cfg<BN, DEEP>;
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
+    constexpr int X_ROWS = LM / CL;                            // rows of x this CTA fetches (and multicasts when CL > 1)
     constexpr int S = C::STAGES;
     constexpr uint32_t IDESC = make_idesc(LM, BN, false);
     constexpr int BOUT = EPI == EPI_SILU ? BN / 2 : BN;       // output columns of this CTA
@@ -116,8 +143,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     const int kt0 = blockIdx.z * p.k_tiles;
     const int nk = p.k_tiles;
 
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
     if (tid == 0) {
-        for (int i = 0; i < 2 * S + 1; ++i) mbar_init(bars + i * 8, 1);
+        for (int i = 0; i < S; ++i) mbar_init(bars + i * 8, 1);                  // full: this CTA's own expect_tx arrival
+        for (int i = S; i < 2 * S; ++i) mbar_init(bars + i * 8, CL);            // empty: one commit per CTA of the cluster
+        mbar_init(bar_done, 1);
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -125,7 +155,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();      // peers' barriers exist before anything is multicast at them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -141,7 +172,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
                 tma_load_2d_hint(dst, &tm_w, bars + slot * 8, kt * LK, blockIdx.x * BN, pol);
             }
         };
-        auto load_x = [&](int slot, int kt) { tma_load_2d(base + slot * C::STAGE, &tm_x, bars + slot * 8, kt * LK, m0); };
+        auto load_x = [&](int slot, int kt) {
+            if constexpr (CL > 1)
+                tma_load_2d_mc(base + slot * C::STAGE + crank * (X_ROWS * 128), &tm_x, bars + slot * 8, kt * LK, m0 + (int)crank * X_ROWS, CL_MASK);
+            else
+                tma_load_2d(base + slot * C::STAGE, &tm_x, bars + slot * 8, kt * LK, m0);
+        };
         const int pre = nk < S ? nk : S;
         for (int i = 0; i < pre; ++i) {                      // weights first: they do not depend on the predecessor
             mbar_expect_tx(bars + i * 8, C::STAGE);
@@ -166,7 +202,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
 #pragma unroll
             for (int ks = 0; ks < LK / 16; ++ks)
                 tc_mma(tmem, make_desc(xs + ks * 32, 16, 1024), make_desc(ws + ks * 32, 16, 1024), IDESC, (i > 0 || ks > 0) ? 1u : 0u);
-            tc_commit(bars + (S + slot) * 8);
+            if constexpr (CL > 1) tc_commit_mc(bars + (S + slot) * 8, CL_MASK);
+            else tc_commit(bars + (S + slot) * 8);
         }
         tc_commit(bar_done);
     }
@@ -203,7 +240,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();      // nobody leaves while a peer may still signal its barriers
+    else __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
 }
 
@@ -290,12 +328,12 @@ bool cached_map(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows
     return true;
 }
 
-template <int BN, int EPI, bool DEEP>
+template <int BN, int EPI, bool DEEP, int CL>
 int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
     using C = Cfg<BN, DEEP>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return B200_ECUDA;
+        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI, DEEP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return B200_ECUDA;
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -303,28 +341,41 @@ int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams&
     cfg.blockDim = dim3(L_THREADS);
     cfg.dynamicSmemBytes = C::SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CL > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CL;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, linear_tc_kernel<BN, EPI, DEEP>, tx, tw, prm) != cudaSuccess) return B200_ECUDA;
+    cfg.numAttrs = na;
+    if (cudaLaunchKernelEx(&cfg, linear_tc_kernel<BN, EPI, DEEP, CL>, tx, tw, prm) != cudaSuccess) return B200_ECUDA;
     return B200_OK;
 }
 
-template <int EPI, bool DEEP>
+template <int EPI, bool DEEP, int CL>
 int dispatch_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
     switch (bn) {
-        case 16: if constexpr (EPI == EPI_SILU) return B200_EUNSUPPORTED; else return launch_linear<16, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
-        case 32: return launch_linear<32, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
-        case 64: return launch_linear<64, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
-        case 128: return launch_linear<128, EPI, DEEP>(tx, tw, prm, grid, pdl, stream);
+        case 16: if constexpr (EPI == EPI_SILU) return B200_EUNSUPPORTED; else return launch_linear<16, EPI, DEEP, CL>(tx, tw, prm, grid, pdl, stream);
+        case 32: return launch_linear<32, EPI, DEEP, CL>(tx, tw, prm, grid, pdl, stream);
+        case 64: return launch_linear<64, EPI, DEEP, CL>(tx, tw, prm, grid, pdl, stream);
+        case 128: return launch_linear<128, EPI, DEEP, CL>(tx, tw, prm, grid, pdl, stream);
         default: return B200_EUNSUPPORTED;
     }
 }
 template <int EPI>
-int dispatch_depth(bool deep, int bn, const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
-    return deep ? dispatch_bn<EPI, true>(bn, tx, tw, prm, grid, pdl, stream) : dispatch_bn<EPI, false>(bn, tx, tw, prm, grid, pdl, stream);
+int dispatch_depth(bool deep, int cluster, int bn, const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
+    if (cluster == 2) return dispatch_bn<EPI, true, 2>(bn, tx, tw, prm, grid, pdl, stream);       // multicast variants: deep ring only
+    if (cluster == 4) return dispatch_bn<EPI, true, 4>(bn, tx, tw, prm, grid, pdl, stream);
+    return deep ? dispatch_bn<EPI, true, 1>(bn, tx, tw, prm, grid, pdl, stream) : dispatch_bn<EPI, false, 1>(bn, tx, tw, prm, grid, pdl, stream);
 }
 
 }  // namespace
@@ -342,8 +393,11 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     if (bout <= 0 || n_out % bout) return B200_EUNSUPPORTED;
     if (rows == 0) return B200_OK;
     const int w_rows = epilogue == EPI_SILU ? 2 * n_out : n_out;
+    const int cluster = 1 << ((flags >> 2) & 3);                         // flags bits 2-3: log2 of the cluster size
+    if (cluster > 4 || (cluster > 1 && (flags & 2))) return B200_EUNSUPPORTED;
+    if ((n_out / bout) % cluster) return B200_EUNSUPPORTED;
     CUtensorMap tx, tw;
-    if (!cached_map(&tx, x, (uint64_t)k, (uint64_t)rows, (uint64_t)x_stride0, LM)) return B200_EUNSUPPORTED;
+    if (!cached_map(&tx, x, (uint64_t)k, (uint64_t)rows, (uint64_t)x_stride0, LM / cluster)) return B200_EUNSUPPORTED;
     if (!cached_map(&tw, w, (uint64_t)k, (uint64_t)w_rows, (uint64_t)k, (uint32_t)bout)) return B200_EUNSUPPORTED;
     LinParams prm;
     prm.out = out;
@@ -357,9 +411,9 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     const bool deep = (flags & 2) == 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    if (epilogue == EPI_BF16) rc = dispatch_depth<EPI_BF16>(deep, block_n, tx, tw, prm, grid, pdl, st);
-    else if (epilogue == EPI_SILU) rc = dispatch_depth<EPI_SILU>(deep, block_n, tx, tw, prm, grid, pdl, st);
-    else rc = dispatch_depth<EPI_PARTIAL>(deep, block_n, tx, tw, prm, grid, pdl, st);
+    if (epilogue == EPI_BF16) rc = dispatch_depth<EPI_BF16>(deep, cluster, block_n, tx, tw, prm, grid, pdl, st);
+    else if (epilogue == EPI_SILU) rc = dispatch_depth<EPI_SILU>(deep, cluster, block_n, tx, tw, prm, grid, pdl, st);
+    else rc = dispatch_depth<EPI_PARTIAL>(deep, cluster, block_n, tx, tw, prm, grid, pdl, st);
     if (rc != B200_OK) return rc;
     return b200_launch_status(nullptr);
 }

@@ -242,7 +242,7 @@ EPI_BF16, EPI_SILU, EPI_PARTIAL = 0, 1, 2
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, block_n: int = 32, k_splits: int = 1,
-           pdl: bool = False, out: torch.Tensor | None = None, shallow: bool = False) -> torch.Tensor:
+           pdl: bool = False, out: torch.Tensor | None = None, shallow: bool = False, cluster: int = 1) -> torch.Tensor:
     """x [rows, k] @ w[n, k]^T on tcgen05.  EPI_SILU: w = [gate; up] rows, returns silu(gate) * up [rows, n/2];
     EPI_PARTIAL: returns fp32 [k_splits, rows, n] partial sums for ``add_rmsnorm_partials``."""
     _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
@@ -256,7 +256,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, block_n: 
             out = torch.empty(rows, n_out, dtype=torch.bfloat16, device=x.device)
     lib = nat.load()
     nat.check(lib.b200_linear(x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(-2), rows, n_out, k,
-                              epilogue, block_n, k_splits, int(pdl) | (2 if shallow else 0), _stream()))
+                              epilogue, block_n, k_splits,
+                              int(pdl) | (2 if shallow else 0) | ({1: 0, 2: 1, 4: 2}[cluster] << 2), _stream()))
     return out
 
 

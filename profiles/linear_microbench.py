@@ -58,9 +58,15 @@ for M in (256, 128, 64, 16, 1):
         r[f"qkv_tc_bn{bn}{'_pdl' if pdl else ''}{'_shallow' if sh else ''}"] = timed(
             lambda i: ops.linear(x_h, w_qkv[i], ops.EPI_BF16, bn, pdl=pdl, shallow=sh))
 
+    for bn, cl in itertools.product((32, 64), (2, 4)):
+        r[f"qkv_tc_bn{bn}_cluster{cl}_pdl"] = timed(lambda i: ops.linear(x_h, w_qkv[i], ops.EPI_BF16, bn, pdl=True, cluster=cl))
+
     r["gate_up+silu_cublas"] = timed(lambda i: ops.silu_mul(F.linear(x_h, w_gu[i])))
     for bn, pdl in itertools.product((32, 64), (False, True)):
         r[f"gate_up+silu_tc_bn{bn}{'_pdl' if pdl else ''}"] = timed(lambda i: ops.linear(x_h, w_gu[i], ops.EPI_SILU, bn, pdl=pdl))
+
+    for bn, cl in itertools.product((32, 64), (2, 4)):
+        r[f"gate_up+silu_tc_bn{bn}_cluster{cl}_pdl"] = timed(lambda i: ops.linear(x_h, w_gu[i], ops.EPI_SILU, bn, pdl=True, cluster=cl))
 
     for name, xin, ws, k in (("o", x_o, w_o, OIN), ("down", x_i, w_dn, INTER)):
         r[f"{name}+addnorm_cublas"] = timed(lambda i: ops.add_rmsnorm(F.linear(xin, ws[i]), resid, wn, 1e-6))

@@ -49,6 +49,21 @@ def test_linear_shallow_ring(block_n):
     assert torch.equal(got, ops.linear(x, w, ops.EPI_BF16, block_n))      # ring depth does not change the arithmetic
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("rows", [1, 100, 256])
+def test_linear_multicast_cluster(cluster, rows):
+    """x tiles fetched once per cluster and multicast to its CTAs: bit-identical to the unclustered kernel."""
+    from nanovllm import ops
+    x, w = _inputs(rows, 4096, 1024, seed=rows + cluster)
+    base = ops.linear(x, w, ops.EPI_BF16, 32)
+    assert torch.equal(ops.linear(x, w, ops.EPI_BF16, 32, cluster=cluster), base)
+    assert torch.equal(ops.linear(x, w, ops.EPI_BF16, 32, cluster=cluster, pdl=True), base)
+    xw, ww = _inputs(rows, 2 * 3072, 1024, seed=7)
+    assert torch.equal(ops.linear(xw, ww, ops.EPI_SILU, 32, cluster=cluster), ops.linear(xw, ww, ops.EPI_SILU, 32))
+    xd, wd = _inputs(rows, 1024, 3072, seed=8)                                    # 48 k tiles, 8 splits, ring wraps
+    assert torch.equal(ops.linear(xd, wd, ops.EPI_PARTIAL, 64, 2, cluster=cluster), ops.linear(xd, wd, ops.EPI_PARTIAL, 64, 2))
+
+
 def test_linear_strided_x():
     from nanovllm import ops
     x, w = _inputs(100, 1024, 1024, seed=5, x_pad=64)       # row stride 1088: a view into a wider buffer
