@@ -58,3 +58,47 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def _header_prototypes():
+    """name -> (return type, [parameter declarations]) parsed from the header."""
+    text = open(os.path.join(ROOT, "include", "b200_paged_attn.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(b200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, params = m.group(1).strip(), m.group(2), m.group(3).strip()
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        protos[name] = (ret, plist)
+    return protos
+
+
+def _ctype_of(decl: str):
+    if "*" in decl:
+        return "ptr"
+    for c_name, kind in (("int64_t", ctypes.c_int64), ("uint64_t", ctypes.c_uint64), ("size_t", ctypes.c_size_t),
+                         ("float", ctypes.c_float), ("int", ctypes.c_int)):
+        if re.search(rf"\b{c_name}\b", decl):
+            return kind
+    raise AssertionError(f"unrecognised C type in {decl!r}")
+
+
+def test_ctypes_table_matches_header_prototypes():
+    """Every argument of every entry point has the width and kind the header declares (a drifted table would corrupt
+    arguments silently)."""
+    protos = _header_prototypes()
+    assert set(protos) == set(nat.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        restype, argtypes = nat.SIGNATURES[name]
+        assert len(argtypes) == len(params), f"{name}: {len(argtypes)} ctypes arguments, header declares {len(params)}"
+        for i, (decl, at) in enumerate(zip(params, argtypes)):
+            want = _ctype_of(decl)
+            if want == "ptr":
+                assert at is ctypes.c_void_p or issubclass(at, ctypes._Pointer), f"{name} arg {i} ({decl}): {at}"
+            else:
+                assert at is want, f"{name} arg {i} ({decl}): table says {at}, header says {want}"
+        if "*" in ret:
+            assert restype in (ctypes.c_char_p, ctypes.c_void_p), name
+        elif ret == "void":
+            assert restype is None, name
+        else:
+            assert restype is _ctype_of(ret), f"{name}: return {ret} vs {restype}"
