@@ -102,3 +102,22 @@ def test_ctypes_table_matches_header_prototypes():
             assert restype is None, name
         else:
             assert restype is _ctype_of(ret), f"{name}: return {ret} vs {restype}"
+
+
+def test_integration_doc_binding_matches_table():
+    """The ctypes stub INTEGRATION.md shows a maintainer is the same binding the product uses."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    text = re.sub(r"\n\s+(?=_)", " ", text)                       # join continued argtypes lines
+    short = {"_vp": ctypes.c_void_p, "_i": ctypes.c_int, "_i64": ctypes.c_int64, "_f": ctypes.c_float, "_sz": ctypes.c_size_t}
+    seen = 0
+    for m in re.finditer(r"_lib\.(b200_\w+)\.argtypes = \[([^\]]*)\]", text):
+        name, args = m.group(1), [a.strip() for a in m.group(2).split(",") if a.strip()]
+        want = nat.SIGNATURES[name][1]
+        assert len(args) == len(want), name
+        for a, w in zip(args, want):
+            if a in short:
+                assert short[a] is w, f"{name}: {a} vs {w}"
+            else:
+                assert "POINTER" in a and issubclass(w, ctypes._Pointer), f"{name}: {a} vs {w}"
+        seen += 1
+    assert seen >= 5
