@@ -121,3 +121,32 @@ def test_integration_doc_binding_matches_table():
                 assert "POINTER" in a and issubclass(w, ctypes._Pointer), f"{name}: {a} vs {w}"
         seen += 1
     assert seen >= 5
+
+
+def test_argument_validation_needs_no_gpu():
+    """Entry points reject bad arguments before touching CUDA (error behaviour is part of the ABI)."""
+    lib = nat.load()
+    EINVAL, EUNSUPPORTED = -1, -2
+    buf = ctypes.create_string_buffer(4096)
+    p = ctypes.addressof(buf) + (-ctypes.addressof(buf)) % 16          # 16-byte aligned scratch address
+    assert lib.b200_silu_mul(None, p, 1, 8, None) == EINVAL
+    assert lib.b200_silu_mul(p, p, 1, 12, None) == EINVAL               # inter must be a multiple of 8
+    assert lib.b200_silu_mul(p + 2, p, 1, 8, None) == EINVAL            # misaligned
+    assert lib.b200_silu_mul(p, p, 0, 8, None) == 0                     # empty batch: nothing to do
+    assert lib.b200_embedding(None, p, p, 1, 8, None) == EINVAL
+    assert lib.b200_gather_tokens(p, None, p, 1, None) == EINVAL
+    assert lib.b200_gather_tokens(p, p, p, 0, None) == 0
+    assert lib.b200_kv_bind(None, p, p, 1, 1, 16, 1, 128) == EINVAL
+    # tensor-parallel exchange: world in [2, 8], rank inside it, row length a multiple of 8 and at most 8192
+    assert lib.b200_allreduce_add_rmsnorm(p, 0, 0, p, p, p, 0, 1, p, p, p, 1, 1024, 1e-6, None) == EINVAL
+    assert lib.b200_allreduce_add_rmsnorm(p, 0, 0, p, p, p, 2, 2, p, p, p, 1, 1024, 1e-6, None) == EINVAL
+    assert lib.b200_allreduce_add_rmsnorm(p, 0, 0, p, p, p, 0, 2, p, p, p, 1, 1001, 1e-6, None) == EUNSUPPORTED
+    assert lib.b200_allreduce_add_rmsnorm(p, 0, 0, p, p, p, 0, 2, p, p, p, 0, 1024, 1e-6, None) == 0
+    # staged linear layer: k a multiple of 64, split-K only with the partial-sum epilogue, block sizes from the list
+    assert lib.b200_linear(None, 64, p, p, 64, 1, 64, 64, 0, 32, 1, 0, None) == EINVAL
+    assert lib.b200_linear(p, 64, p, p, 64, 1, 64, 96, 0, 32, 1, 0, None) == EUNSUPPORTED
+    assert lib.b200_linear(p, 128, p, p, 64, 1, 64, 128, 0, 32, 2, 0, None) == EINVAL
+    assert lib.b200_linear(p, 64, p, p, 64, 1, 48, 64, 0, 32, 1, 0, None) == EUNSUPPORTED
+    assert lib.b200_linear(p, 64, p, p, 64, 0, 64, 64, 0, 32, 1, 0, None) == 0
+    assert lib.b200_add_rmsnorm_partials(None, 1, p, p, p, 1, 64, 1e-6, 0, None) == EINVAL
+    assert lib.b200_add_rmsnorm_partials(p, 1, p, p, p, 1, 10000, 1e-6, 0, None) == EUNSUPPORTED
