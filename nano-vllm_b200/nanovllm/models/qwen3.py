@@ -79,7 +79,7 @@ class Qwen3ForCausalLM:
         # Staged for the next round and OFF by default: B200_LINEAR=tc routes the decode-size projections through
         # csrc/linear_tc.cu (tcgen05, SiluAndMul / split-K add+RMSNorm fused) instead of cuBLAS.  That kernel has not
         # run on a GPU yet.  B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
-        self.tc_linear = os.environ.get("B200_LINEAR", "cublas") == "tc" and tp_size == 1
+        self.tc_linear = os.environ.get("B200_LINEAR", "cublas") == "tc"
         self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "32,32,64,8,64,8,0").split(",")]
         self.tc_max_rows = 256
         if getattr(c, "attention_bias", False):
@@ -155,9 +155,13 @@ class Qwen3ForCausalLM:
     def _row_linear(self, x: torch.Tensor, w: torch.Tensor, tc=None):
         """Row-parallel GEMM (o_proj / down_proj).  Returns (partial, where): where is True when the partial sits in
         the peer-mapped buffer, "parts" when it is the fp32 split-K partials of the staged tcgen05 path."""
-        if tc is not None:
-            return ops.linear(x, w, ops.EPI_PARTIAL, tc[0], tc[1], pdl=bool(self.tc_cfg[6])), "parts"
         peer = self.peer
+        if tc is not None and self.tp_size == 1:
+            return ops.linear(x, w, ops.EPI_PARTIAL, tc[0], tc[1], pdl=bool(self.tc_cfg[6])), "parts"
+        if tc is not None:           # tensor parallel: K is already divided by the ranks; write bf16 straight into the peer buffer
+            out = peer.next_out(x.shape[0])
+            ops.linear(x, w, ops.EPI_BF16, min(tc[0], 32), pdl=bool(self.tc_cfg[6]), out=out)
+            return out, True
         if peer is not None and x.shape[0] <= peer.rows_cap:
             out = peer.next_out(x.shape[0])
             torch.mm(x, w.t(), out=out)
@@ -181,7 +185,8 @@ class Qwen3ForCausalLM:
         h = ops.embedding(input_ids, self.embed)
         residual, in_peer = None, False
         cfg = self.tc_cfg
-        tc = self.tc_linear and h.shape[0] <= self.tc_max_rows
+        tc = self.tc_linear and h.shape[0] <= self.tc_max_rows and (
+            self.tp_size == 1 or (self.peer is not None and h.shape[0] <= self.peer.rows_cap))
         for li, L in enumerate(self.layers):
             attn = self.attn[li]
             if residual is None:
