@@ -88,6 +88,40 @@ def workloads() -> dict:
     return out
 
 
+def fuzz_workloads(seed: int, n: int) -> list:
+    """Small random workloads for differential testing (tests/test_differential_fuzz.py): every knob the scheduler
+    and the block manager branch on is drawn at random -- page size, token budget, running slots, cache size (tight
+    enough to preempt), shared prefixes and exact duplicates (prefix-cache hits, block revival), EOS stops."""
+    out = []
+    for i in range(n):
+        r = random.Random(seed * 100003 + i)
+        bs = r.choice([2, 4, 8, 16, 32, 256])      # not 1: the reference's `len % block_size == 1` append rule needs >= 2
+        nseq = r.randint(1, 40)
+        max_len = r.choice([8, 40, 150, 600])
+        vocab = r.choice([5, 37, 1000, 50000])
+        prefixes = [[r.randrange(vocab) for _ in range(r.randint(0, 3 * bs + 5))] for _ in range(3)]
+        prompts = []
+        for _ in range(nseq):
+            kind = r.random()
+            if kind < 0.15 and prompts:
+                prompts.append(list(r.choice(prompts)))                        # exact duplicate
+            elif kind < 0.55:
+                prompts.append(r.choice(prefixes) + [r.randrange(vocab) for _ in range(r.randint(1, max_len))])
+            else:
+                prompts.append([r.randrange(vocab) for _ in range(r.randint(1, max_len))])
+        use_eos = r.random() < 0.4
+        sps = [(r.choice([0.5, 0.8, 1.0]), r.randint(1, 40), not use_eos or r.random() < 0.3) for _ in range(nseq)]
+        longest = max(len(p) + mt for p, (_, mt, _) in zip(prompts, sps))
+        need = (longest + bs - 1) // bs + 1                                    # one sequence must always fit
+        total = sum((len(p) + mt + bs - 1) // bs for p, (_, mt, _) in zip(prompts, sps))
+        nblk = max(need, int(total * r.choice([0.15, 0.4, 1.0, 2.0])))
+        budget = r.choice([16, 64, 256, 4096])
+        cfg = dict(max_num_seqs=r.choice([1, 2, 5, 16, 64]), max_num_batched_tokens=budget, kvcache_block_size=bs,
+                   num_kvcache_blocks=nblk)
+        out.append(dict(cfg=cfg, prompts=prompts, sps=sps, vocab=vocab, eos=r.randrange(vocab) if use_eos else -1))
+    return out
+
+
 def digest(*arrays) -> str:
     h = hashlib.sha256()
     for a in arrays:
@@ -196,6 +230,24 @@ def gen_traces(torch, only=None):
         print(name, {k: v for k, v in rec.items() if k != "steps"})
 
 
+def fuzz_reference(torch, seed: int, n: int, out_path: str):
+    """Reference side of the differential test: run the reference's classes over fuzz_workloads(seed, n)."""
+    import itertools
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    from nanovllm.sampling_params import SamplingParams
+    results = []
+    for w in fuzz_workloads(seed, n):
+        cfg = types.SimpleNamespace(eos=w["eos"], **w["cfg"])
+        Sequence.block_size = cfg.kvcache_block_size
+        Sequence.counter = itertools.count()
+        make_seq = lambda p, t, mt, ie: Sequence(p, SamplingParams(temperature=t, max_tokens=mt, ignore_eos=ie))
+        rec = drive(make_seq, Scheduler(cfg), cfg.kvcache_block_size, reference_meta_builder(torch, cfg.kvcache_block_size), w)
+        results.append(rec)
+    with open(out_path, "w") as f:
+        json.dump(results, f)
+
+
 def gen_hash_kat():
     from nanovllm.engine.block_manager import BlockManager
     rnd = random.Random(1)
@@ -276,6 +328,9 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch = import_reference()
     only = sys.argv[1:]                      # e.g. `make_golden.py mixed1024 longctx128` regenerates just those traces
+    if only and only[0] == "--fuzz":         # `make_golden.py --fuzz SEED N OUT.json` (tests/test_differential_fuzz.py)
+        fuzz_reference(torch, int(only[1]), int(only[2]), only[3])
+        return
     if only:
         gen_traces(torch, only)
         return
