@@ -87,3 +87,45 @@ def test_overlapped_loop_equals_reference_trace(name, golden_dir):
         assert eng.model_runner.early > 0
     else:
         assert eng.model_runner.early == 0
+
+
+@pytest.mark.parametrize("seed", [3])
+def test_overlapped_loop_equals_synchronous_loop_on_random_workloads(seed):
+    """The same property on 120 random workloads (oracle.make_golden.fuzz_workloads: mixed ignore_eos / EOS batches,
+    preemption, chunking, prefix hits): the overlapped loop must issue exactly the steps of the synchronous
+    schedule -> run -> postprocess loop.  Needs no reference: the synchronous loop is pinned to it elsewhere."""
+    from oracle.make_golden import drive, fuzz_workloads
+    from nanovllm.engine.llm_engine import LLMEngine
+    from nanovllm.engine.scheduler import Scheduler
+    from nanovllm.engine.sequence import Sequence
+    from nanovllm.sampling_params import SamplingParams
+    from test_bookkeeping_golden import product_meta_builder
+    early = 0
+    for i, w in enumerate(fuzz_workloads(seed, 120)):
+        cfg = types.SimpleNamespace(eos=w["eos"], **w["cfg"])
+        make = lambda p, t, mt, ie: Sequence(p, SamplingParams(temperature=t, max_tokens=mt, ignore_eos=ie))
+        Sequence.block_size = cfg.kvcache_block_size
+        Sequence.counter = itertools.count()
+        sync = drive(make, Scheduler(cfg), cfg.kvcache_block_size, product_meta_builder(cfg.kvcache_block_size), w)
+
+        Sequence.counter = itertools.count()
+        eng = object.__new__(LLMEngine)
+        eng.scheduler = Scheduler(cfg)
+        eng.model_runner = FakeRunner(cfg.kvcache_block_size, w["vocab"])
+        for p, (t, mt, ie) in zip(w["prompts"], w["sps"]):
+            eng.scheduler.add(make(p, t, mt, ie))
+        outputs = {}
+
+        def on_step(finished, num_tokens, dt, outputs=outputs):
+            for s in finished:
+                assert -1 not in s.completion_token_ids
+                outputs[s.seq_id] = list(s.completion_token_ids)
+
+        eng._run_overlapped(on_step)
+        got = eng.model_runner.steps
+        assert len(got) == sync["num_steps"], f"workload {i}: {w['cfg']}"
+        for k, (a, b) in enumerate(zip(got, sync["steps"])):
+            assert a == b, f"workload {i} ({w['cfg']}), step {k}: overlapped {a} != synchronous {b}"
+        assert digest(*[np.asarray(outputs[k]) for k in sorted(outputs)]) == sync["outputs"]
+        early += eng.model_runner.early
+    assert early > 500          # the early-launch path was exercised, not just the synchronous fallback
