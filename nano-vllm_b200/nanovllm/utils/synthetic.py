@@ -27,6 +27,10 @@ PRESETS = {
                  head_dim=128, intermediate_size=512, vocab_size=2048, tie_word_embeddings=True),
     "tiny-g4": dict(hidden_size=256, num_hidden_layers=3, num_attention_heads=8, num_key_value_heads=2,
                     head_dim=128, intermediate_size=768, vocab_size=4096, tie_word_embeddings=False),
+    "tiny-g1": dict(hidden_size=192, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=2,
+                    head_dim=128, intermediate_size=320, vocab_size=1024, tie_word_embeddings=True),
+    "tiny-g8": dict(hidden_size=320, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=1,
+                    head_dim=128, intermediate_size=448, vocab_size=3072, tie_word_embeddings=False),
 }
 
 

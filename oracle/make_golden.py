@@ -39,6 +39,9 @@ sys.path.insert(0, ROOT)
 # --------------------------------------------------------------------------------------------
 # shared with tests/: workload definitions and the digest format
 # --------------------------------------------------------------------------------------------
+MODEL_PRESETS = ("tiny", "tiny-g4", "tiny-g1", "tiny-g8")      # q/kv head ratios 2, 4, 1, 8; tied and untied LM heads
+
+
 def fake_token(seq_id: int, num_tokens: int, vocab: int) -> int:
     return (seq_id * 7919 + num_tokens * 104729 + 13) % vocab
 
@@ -328,6 +331,10 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch = import_reference()
     only = sys.argv[1:]                      # e.g. `make_golden.py mixed1024 longctx128` regenerates just those traces
+    if only and only[0] == "--models":       # `make_golden.py --models tiny-g1 tiny-g8`: just those model fixtures
+        for preset in only[1:]:
+            gen_model(torch, preset)
+        return
     if only and only[0] == "--fuzz":         # `make_golden.py --fuzz SEED N OUT.json` (tests/test_differential_fuzz.py)
         fuzz_reference(torch, int(only[1]), int(only[2]), only[3])
         return
@@ -336,7 +343,7 @@ def main():
         return
     gen_hash_kat()
     gen_traces(torch)
-    for preset in ("tiny", "tiny-g4"):
+    for preset in MODEL_PRESETS:
         gen_model(torch, preset)
 
 

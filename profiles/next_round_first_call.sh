@@ -5,6 +5,7 @@
 mkdir -p gpurun_out
 # 1. changes made after the last validated GPU run: golden-logit comparison, peer-exchange timeout / self-test plumbing
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/nr_gpu_tests.log 2>&1; echo "gpu tests rc=$?" >> gpurun_out/nr_gpu_tests.log
+B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_model.py -m gpu -q -k "tiny-g1 or tiny-g8" > gpurun_out/nr_model_g1_g8.log 2>&1
 # 2. the staged tcgen05 linear layer: parity first, then the sweep, then the whole model through it
 B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_linear.py -m gpu -x -q > gpurun_out/nr_linear_tests.log 2>&1
 rc=$?; echo "linear tests rc=$rc" >> gpurun_out/nr_linear_tests.log

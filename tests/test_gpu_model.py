@@ -1,5 +1,6 @@
 """Whole-model and engine parity on the GPU: product forward (CUDA kernels + cuBLAS) vs the CPU oracle
 that tests/test_oracle_golden.py pinned to the reference's own modules."""
+import os
 import random
 from types import SimpleNamespace
 
@@ -11,6 +12,9 @@ from oracle.model_script import make_script, run_script
 from oracle.qwen3_ref import alloc_logical_kv
 
 pytestmark = pytest.mark.gpu
+
+# presets added after the last GPU run of the round: opt-in until they have been seen green once
+_new = pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1", reason="not yet run on a GPU: set B200_EXPERIMENTAL=1")
 
 
 def build_product_model(preset, weights, nblk, bs):
@@ -29,7 +33,7 @@ def build_product_model(preset, weights, nblk, bs):
     return model, kv
 
 
-@pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g4", pytest.param("tiny-g1", marks=_new), pytest.param("tiny-g8", marks=_new)])
 def test_model_script_vs_oracle(preset):
     from nanovllm.utils.context import reset_context, set_context
     from nanovllm.utils.synthetic import PRESETS, random_weights

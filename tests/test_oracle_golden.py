@@ -26,7 +26,7 @@ def oracle_step_fn(model, kv):
     return step
 
 
-@pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g4", "tiny-g1", "tiny-g8"])
 def test_qwen3_ref_equals_reference_modules(preset, golden_dir):
     gold = np.load(os.path.join(golden_dir, f"model_{preset}.npz"))
     dims = RefDims.from_json(hf_config_dict(PRESETS[preset]))
