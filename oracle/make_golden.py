@@ -251,6 +251,40 @@ def fuzz_reference(torch, seed: int, n: int, out_path: str):
         json.dump(results, f)
 
 
+def api_surface(pkg) -> dict:
+    """Public API of a `nanovllm` package as plain data (same function runs on the reference and on the product)."""
+    import dataclasses
+    import inspect
+    from nanovllm.config import Config
+    from nanovllm.engine.llm_engine import LLMEngine
+    from nanovllm.sampling_params import SamplingParams
+
+    def fields(cls):
+        out = []
+        for f in dataclasses.fields(cls):
+            default = repr(f.default) if f.default is not dataclasses.MISSING else "<required>"
+            out.append([f.name, default])
+        return out
+
+    def params(fn):
+        out = []
+        for name, p in inspect.signature(fn).parameters.items():
+            out.append([name, "<required>" if p.default is inspect.Parameter.empty else repr(p.default), p.kind.name])
+        return out
+
+    methods = {m: params(getattr(LLMEngine, m)) for m in ("__init__", "add_request", "step", "is_finished", "generate", "exit")}
+    return dict(exports=sorted(n for n in ("LLM", "SamplingParams") if hasattr(pkg, n)),
+                llm_is_engine=issubclass(pkg.LLM, LLMEngine),
+                config=fields(Config), sampling_params=fields(SamplingParams), engine_methods=methods)
+
+
+def gen_api_surface():
+    import nanovllm
+    with open(os.path.join(GOLD, "api_surface.json"), "w") as f:
+        json.dump(api_surface(nanovllm), f, indent=1)
+    print("api surface written")
+
+
 def gen_hash_kat():
     from nanovllm.engine.block_manager import BlockManager
     rnd = random.Random(1)
@@ -331,6 +365,9 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch = import_reference()
     only = sys.argv[1:]                      # e.g. `make_golden.py mixed1024 longctx128` regenerates just those traces
+    if only and only[0] == "--api":
+        gen_api_surface()
+        return
     if only and only[0] == "--models":       # `make_golden.py --models tiny-g1 tiny-g8`: just those model fixtures
         for preset in only[1:]:
             gen_model(torch, preset)
@@ -342,6 +379,7 @@ def main():
         gen_traces(torch, only)
         return
     gen_hash_kat()
+    gen_api_surface()
     gen_traces(torch)
     for preset in MODEL_PRESETS:
         gen_model(torch, preset)

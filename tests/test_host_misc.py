@@ -57,3 +57,32 @@ def test_llm_ignores_unknown_keywords_and_needs_a_gpu(tmp_path):
         pytest.skip("GPU present")
     with pytest.raises(B200Error):
         LLM(d, enforce_eager=True, not_a_config_field=123, kvcache_block_size=16)
+
+
+def test_public_api_matches_reference_surface(golden_dir):
+    """tests/golden/api_surface.json is the reference's public surface (oracle/make_golden.py --api, by introspection of
+    the reference package): exports, Config / SamplingParams fields with defaults, the engine's public methods with
+    parameter names and defaults.  The product must offer all of it unchanged; it may add optional extras at the end."""
+    import json
+    import os
+    import nanovllm
+    from oracle.make_golden import api_surface
+    ref = json.load(open(os.path.join(golden_dir, "api_surface.json")))
+    got = api_surface(nanovllm)
+    assert got["exports"] == ref["exports"] and got["llm_is_engine"] == ref["llm_is_engine"]
+    for section in ("config", "sampling_params"):
+        mine = {name: default for name, default in got[section]}
+        for name, default in ref[section]:
+            assert name in mine, f"{section}.{name} missing"
+            if (section, name) == ("config", "num_kvcache_blocks"):
+                assert mine[name] in ("-1", "None")          # both mean "size the cache from free memory"
+            else:
+                assert mine[name] == default, f"{section}.{name}: default {mine[name]} vs reference {default}"
+        # field ORDER matters for positional construction
+        names = [n for n, _ in got[section]]
+        assert names[:len(ref[section])] == [n for n, _ in ref[section]], section
+    for method, params in ref["engine_methods"].items():
+        mine = got["engine_methods"][method]
+        assert mine[:len(params)] == params, f"{method}: {mine} vs reference {params}"
+        for extra in mine[len(params):]:
+            assert extra[1] != "<required>" or extra[2] == "VAR_KEYWORD", f"{method}: extra required parameter {extra}"
