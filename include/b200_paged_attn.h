@@ -211,6 +211,19 @@ int b200_sample(const void* logits, int logits_is_fp32, int64_t logits_stride0,
 int b200_linear(const void* x, int64_t x_stride0, const void* w, void* out, int64_t out_stride0, int rows,
                 int n_out, int k, int epilogue, int block_n, int k_splits, int flags, void* stream);
 
+/* (staged) ParallelLMHead.forward + Sampler.forward in one pass (layers/embed_head.py:56-66, layers/sampler.py:7-12):
+ * logits = bf16(hidden lm_head^T) are produced tile by tile in tensor memory, scored exactly as b200_sample scores
+ * them (same RNG keyed by (seed, step, row, vocabulary id); temperature 0 = greedy, lowest index on ties) and
+ * reduced to one packed (score, token) key per row with atomicMax -- the [rows, vocab] logits are never written.
+ *   hidden [rows, k] bf16 (last-token rows), lm_head [vocab, k] bf16 contiguous (this rank's shard), k % 64 == 0;
+ *   vocab may be ragged with respect to block_n (16/32/64/128); key_workspace: rows x uint64, ZERO on entry, left
+ *   zero on exit (a second tiny kernel turns keys into out / out_keys and clears them);
+ *   out / out_keys / index_offset / seed / step / step_dev: as b200_sample.  flags: as b200_linear. */
+int b200_lm_head_sample(const void* hidden, int64_t hidden_stride0, const void* lm_head, int rows, int vocab, int k,
+                        const float* temperatures, int64_t index_offset, uint64_t seed, uint64_t step,
+                        const int64_t* step_dev, void* key_workspace, int64_t* out, int64_t* out_keys, int block_n,
+                        int flags, void* stream);
+
 /* RMSNorm.add_rms_forward (layers/layernorm.py:28-40) whose input is a split-K projection:
  *   h = bf16(sum_s partials[s]) in split order (deterministic), then as b200_add_rmsnorm.  cols <= 8192. */
 int b200_add_rmsnorm_partials(const float* partials, int splits, void* residual, const void* weight, void* out,

@@ -24,6 +24,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "sample_common.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -35,7 +36,7 @@ constexpr int LK = 64;                    // k extent of a ring slot: one 128-by
 constexpr int L_THREADS = 128;
 constexpr uint32_t X_TILE = LM * 128;     // 16 KB
 
-enum { EPI_BF16 = 0, EPI_SILU = 1, EPI_PARTIAL = 2 };
+enum { EPI_BF16 = 0, EPI_SILU = 1, EPI_PARTIAL = 2, EPI_SAMPLE = 3 };
 
 // DEEP: as many ring slots as one CTA per SM allows (all of a short K in flight).  !DEEP: 4 slots for block_n <= 64, so
 // that two CTAs fit an SM and a dependent kernel launched early (PDL) finds room to prefetch its weights.
@@ -55,6 +56,13 @@ struct LinParams {
     int rows;                 // M
     int up_row0;              // EPI_SILU: first W row of the "up" half (= inter)
     int k_tiles;              // 64-wide k tiles per split (gridDim.z splits)
+    // EPI_SAMPLE (fused LM head + sampling): nothing of size [rows, vocab] is ever written
+    int n_valid;                          // columns of this vocabulary shard (the last column block may be ragged)
+    const float* temperatures;            // [rows] or null (greedy)
+    int64_t index_offset;                 // first vocabulary id of the shard
+    uint64_t seed, step;
+    const int64_t* step_dev;              // optional device-side addend to step (CUDA-graph replays)
+    unsigned long long* keys;             // [rows] running maximum of packed (score, token) keys; zero = empty
 };
 
 __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint64_t policy) {
@@ -215,7 +223,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     float acc[BN];
     load_acc_row<BN>(tmem + ((uint32_t)(warp * 32) << 16), acc);
     const int row = m0 + tid;
-    if (row < p.rows) {
+    if constexpr (EPI == EPI_SAMPLE) {
+        // LM head + Sampler.forward in one pass (layers/embed_head.py:56-66, layers/sampler.py:7-12): this thread holds
+        // BN logits of its row; they are rounded to bf16 (the reference's logits are the bf16 output of F.linear), scored
+        // (greedy: the logit; otherwise the exponential race) and only the best (score, token) key leaves the SM.
+        if (row < p.rows) {
+            const uint64_t step = p.step + (p.step_dev ? (uint64_t)*p.step_dev : 0ull);
+            const b200sample::RowSampler rs(p.temperatures ? p.temperatures[row] : 0.f, p.seed, step, row);
+            b200sample::Best best{-INFINITY, 0x7fffffff};
+            const int n0 = blockIdx.x * BN;
+#pragma unroll
+            for (int c = 0; c < BN; ++c) {
+                const int col = n0 + c;
+                if (col < p.n_valid) b200sample::take(best, rs.score(round_bf16(acc[c]), p.index_offset + col), col);
+            }
+            if (best.i != 0x7fffffff)
+                atomicMax(p.keys + row, b200sample::pack_key(best.v, (uint32_t)(p.index_offset + best.i)));
+        }
+    } else if (row < p.rows) {
         if constexpr (EPI == EPI_PARTIAL) {
             float* dst = static_cast<float*>(p.out) + ((int64_t)blockIdx.z * p.rows + row) * p.out_stride + blockIdx.x * BN;
 #pragma unroll
@@ -297,6 +322,18 @@ __global__ void __launch_bounds__(PN_THREADS) add_rmsnorm_partials_kernel(const 
             o4[idx] = pack8(y);
         }
     }
+}
+
+// keys -> token ids (and the signed keys of the vocab-parallel combine); leaves the key array empty for the next step
+__global__ void sample_finalize_kernel(unsigned long long* keys, int64_t* out, int64_t* out_keys, int64_t index_offset, int rows) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const unsigned long long key = keys[row];
+    keys[row] = 0ull;
+    if (out) out[row] = key ? (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull)) : index_offset;
+    if (out_keys) out_keys[row] = (int64_t)(key ^ 0x8000000000000000ull);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -399,7 +436,7 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     CUtensorMap tx, tw;
     if (!cached_map(&tx, x, (uint64_t)k, (uint64_t)rows, (uint64_t)x_stride0, LM / cluster)) return B200_EUNSUPPORTED;
     if (!cached_map(&tw, w, (uint64_t)k, (uint64_t)w_rows, (uint64_t)k, (uint32_t)bout)) return B200_EUNSUPPORTED;
-    LinParams prm;
+    LinParams prm = {};
     prm.out = out;
     prm.out_stride = out_stride0;
     prm.rows = rows;
@@ -415,6 +452,50 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     else if (epilogue == EPI_SILU) rc = dispatch_depth<EPI_SILU>(deep, cluster, block_n, tx, tw, prm, grid, pdl, st);
     else rc = dispatch_depth<EPI_PARTIAL>(deep, cluster, block_n, tx, tw, prm, grid, pdl, st);
     if (rc != B200_OK) return rc;
+    return b200_launch_status(nullptr);
+}
+
+extern "C" int b200_lm_head_sample(const void* hidden, int64_t hidden_stride0, const void* lm_head, int rows, int vocab, int k,
+                                   const float* temperatures, int64_t index_offset, uint64_t seed, uint64_t step,
+                                   const int64_t* step_dev, void* key_workspace, int64_t* out, int64_t* out_keys, int block_n,
+                                   int flags, void* stream) {
+    if (!hidden || !lm_head || !key_workspace || (!out && !out_keys) || rows < 0 || vocab <= 0 || k <= 0 || index_offset < 0) return B200_EINVAL;
+    if (((uintptr_t)hidden & 15) || ((uintptr_t)lm_head & 15) || ((uintptr_t)key_workspace & 7) || (hidden_stride0 % 8)) return B200_EINVAL;
+    if (index_offset + vocab > 0xffffffffll || (k % LK)) return B200_EUNSUPPORTED;
+    if (rows == 0) return B200_OK;
+    const int cluster = 1 << ((flags >> 2) & 3);
+    if (cluster > 4 || (cluster > 1 && (flags & 2))) return B200_EUNSUPPORTED;
+    const int n_tiles = (vocab + block_n - 1) / block_n;
+    if (block_n <= 0 || n_tiles % cluster) return B200_EUNSUPPORTED;
+    CUtensorMap tx, tw;
+    if (!cached_map(&tx, hidden, (uint64_t)k, (uint64_t)rows, (uint64_t)hidden_stride0, LM / cluster)) return B200_EUNSUPPORTED;
+    if (!cached_map(&tw, lm_head, (uint64_t)k, (uint64_t)vocab, (uint64_t)k, (uint32_t)block_n)) return B200_EUNSUPPORTED;
+    LinParams prm = {};
+    prm.rows = rows;
+    prm.k_tiles = k / LK;
+    prm.n_valid = vocab;
+    prm.temperatures = temperatures;
+    prm.index_offset = index_offset;
+    prm.seed = seed;
+    prm.step = step;
+    prm.step_dev = step_dev;
+    prm.keys = static_cast<unsigned long long*>(key_workspace);
+    dim3 grid(n_tiles, (rows + LM - 1) / LM, 1);
+    if (grid.y > 65535) return B200_EUNSUPPORTED;
+    const bool pdl = (flags & 1) != 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = dispatch_depth<EPI_SAMPLE>((flags & 2) == 0, cluster, block_n, tx, tw, prm, grid, pdl, st);
+    if (rc != B200_OK) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((rows + 127) / 128);
+    cfg.blockDim = dim3(128);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, sample_finalize_kernel, prm.keys, out, out_keys, index_offset, rows) != cudaSuccess) return B200_ECUDA;
     return b200_launch_status(nullptr);
 }
 

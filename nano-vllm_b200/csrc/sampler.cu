@@ -7,9 +7,11 @@
 // fills many SMs); slices leave packed (score, index) keys in a static scratch array and the last CTA
 // to finish a row (self-resetting counter) folds them.  Ties go to the lowest index at every level, so
 // the result does not depend on the split count.
-#include "common.cuh"
+#include "sample_common.cuh"
 
 namespace {
+
+using namespace b200sample;
 
 constexpr int SAMPLE_THREADS = 256;
 constexpr int MAX_SPLITS = 16;
@@ -17,32 +19,6 @@ constexpr int MAX_ROWS_SPLIT = 1024;
 
 __device__ unsigned long long g_slice_keys[MAX_ROWS_SPLIT * MAX_SPLITS];
 __device__ unsigned int g_row_done[MAX_ROWS_SPLIT];
-
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {   // 32-bit avalanche (two multiplies)
-    x ^= x >> 16; x *= 0x7feb352du;
-    x ^= x >> 15; x *= 0x846ca68bu;
-    x ^= x >> 16;
-    return x;
-}
-
-struct Best {
-    float v;
-    int i;
-};
-__device__ __forceinline__ void take(Best& b, float v, int i) {
-    if (v > b.v || (v == b.v && i < b.i)) { b.v = v; b.i = i; }
-}
-// order-preserving packing: larger key <=> larger score, then lower index
-__device__ __forceinline__ unsigned long long pack_key(float v, uint32_t idx) {
-    uint32_t bits = __float_as_uint(v);
-    bits ^= (bits >> 31) ? 0xffffffffu : 0x80000000u;
-    return ((unsigned long long)bits << 32) | (unsigned long long)(0xffffffffu - idx);
-}
 
 template <bool FP32>
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const void* __restrict__ logits, int64_t stride,

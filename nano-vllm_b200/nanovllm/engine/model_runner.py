@@ -177,6 +177,8 @@ class ModelRunner:
         self._host_k = 0
         self.g_tokens = torch.zeros(S, dtype=torch.int64, device="cuda")
         self.g_keys = torch.zeros(S, dtype=torch.int64, device="cuda")
+        self.g_keyws = torch.zeros(S, dtype=torch.int64, device="cuda")      # running-max keys of the fused LM head (zero between steps)
+        self.fused_lm_head = os.environ.get("B200_LM_HEAD", "gemm") == "fused"
         self.h_tokens = [torch.empty(S, dtype=torch.int64, pin_memory=True) for _ in range(2)]
         self.h_tokens_np = [t.numpy() for t in self.h_tokens]
         self.h2d_bytes_last = 0
@@ -367,6 +369,19 @@ class ModelRunner:
     def _forward_and_sample(self, input_ids, positions, temps, step_dev, rows: int):
         """hidden -> shard logits -> sampled token ids in self.g_tokens[:rows] (all enqueued, no sync)."""
         hidden = self.model(input_ids, positions)
+        if self.fused_lm_head and rows <= self.g_keyws.numel():
+            # staged, opt-in (B200_LM_HEAD=fused): LM head + sampling in one tensor-core kernel, logits never written
+            last = self.model.last_token_rows(hidden)
+            if self.world_size == 1:
+                ops.lm_head_sample(last, self.model.lm_head, temps, self.sample_seed, 0, self.g_keyws, out=self.g_tokens[:rows],
+                                   step_dev=step_dev)
+            else:
+                keys = self.g_keys[:rows]
+                ops.lm_head_sample(last, self.model.lm_head, temps, self.sample_seed, 0, self.g_keyws, out=self.g_tokens[:rows],
+                                   index_offset=self.vocab_offset, out_keys=keys, step_dev=step_dev)
+                dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+                self.g_tokens[:rows].copy_(ops.tokens_from_keys(keys))
+            return
         logits = self.model.compute_logits(hidden)
         if self.world_size == 1:
             ops.sample(logits, temps, self.sample_seed, 0, out=self.g_tokens[:rows], step_dev=step_dev)

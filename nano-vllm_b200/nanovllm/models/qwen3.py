@@ -220,10 +220,15 @@ class Qwen3ForCausalLM:
     __call__ = forward
 
     @torch.inference_mode()
-    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
-        """Logits of this rank's vocab shard for the last token of every sequence (embed_head.py:56-61)."""
+    def last_token_rows(self, hidden: torch.Tensor) -> torch.Tensor:
+        """The hidden state of the last token of every sequence (embed_head.py:58-60)."""
         ctx = get_context()
         if ctx.is_prefill:
             last = (ctx.cu_seqlens_q[1:] - 1).to(torch.long)
             hidden = hidden.index_select(0, last)
-        return F.linear(hidden, self.lm_head)
+        return hidden
+
+    @torch.inference_mode()
+    def compute_logits(self, hidden: torch.Tensor) -> torch.Tensor:
+        """Logits of this rank's vocab shard for the last token of every sequence (embed_head.py:56-61)."""
+        return F.linear(self.last_token_rows(hidden), self.lm_head)

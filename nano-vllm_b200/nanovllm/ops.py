@@ -274,3 +274,24 @@ def add_rmsnorm_partials(partials: torch.Tensor, residual: torch.Tensor, weight:
     nat.check(lib.b200_add_rmsnorm_partials(partials.data_ptr(), splits, residual.data_ptr(), weight.data_ptr(), out.data_ptr(),
                                             rows, cols, eps, int(pdl), _stream()))
     return out, residual
+
+
+def lm_head_sample(hidden: torch.Tensor, lm_head: torch.Tensor, temperatures: torch.Tensor | None, seed: int, step: int,
+                   key_workspace: torch.Tensor, out: torch.Tensor | None = None, index_offset: int = 0,
+                   out_keys: torch.Tensor | None = None, step_dev: torch.Tensor | None = None, block_n: int = 128,
+                   pdl: bool = False, shallow: bool = True, cluster: int = 1) -> torch.Tensor:
+    """Fused LM head + sampling: hidden [rows, k] x lm_head [vocab, k] -> token ids, without materialising the logits.
+    ``key_workspace``: int64/uint64 [>= rows], zero before the call, zero again after it."""
+    _need(hidden, torch.bfloat16, "hidden"); _need(lm_head, torch.bfloat16, "lm_head")
+    assert hidden.dim() == 2 and hidden.stride(1) == 1 and lm_head.is_contiguous() and hidden.shape[1] == lm_head.shape[1]
+    assert key_workspace.is_cuda and key_workspace.element_size() == 8 and key_workspace.numel() >= hidden.shape[0]
+    rows, k = hidden.shape
+    if out is None and out_keys is None:
+        out = torch.empty(rows, dtype=torch.int64, device=hidden.device)
+    lib = nat.load()
+    flags = int(pdl) | (2 if shallow and cluster == 1 else 0) | ({1: 0, 2: 1, 4: 2}[cluster] << 2)
+    nat.check(lib.b200_lm_head_sample(hidden.data_ptr(), hidden.stride(0), lm_head.data_ptr(), rows, lm_head.shape[0], k,
+                                      _ptr(temperatures), index_offset, seed & (2**64 - 1), step & (2**64 - 1), _ptr(step_dev),
+                                      key_workspace.data_ptr(), _ptr(out), _ptr(out_keys), block_n, flags, _stream()))
+    LAUNCHES[0] += 1                      # two kernels behind one call
+    return out if out is not None else out_keys

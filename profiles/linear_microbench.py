@@ -88,6 +88,15 @@ for M in (256, 128, 64, 16, 1):
     r["mlp_chain_cublas"] = timed(mlp_lib)
     r["mlp_chain_tc_pdl"] = timed(mlp_tc)
     r["mlp_chain_tc_nopdl"] = timed(lambda i: mlp_tc(i, False))
+    # LM head + sampling (tied Qwen3-0.6B head: 151 936 x 1024), two distinct weight sets (311 MB each)
+    heads = [rnd(151936, HID) for _ in range(2)]
+    temps = torch.full((M,), 0.6, device="cuda")
+    kws = torch.zeros(M, dtype=torch.int64, device="cuda")
+    r["lm_head+sample_cublas"] = timed(lambda i: ops.sample(F.linear(x_h, heads[i]), temps, 1, 0), nsets=2)
+    for sh, cl in ((True, 1), (False, 1), (False, 2), (False, 4)):
+        r[f"lm_head+sample_fused_{'shallow' if sh else 'deep'}_cluster{cl}"] = timed(
+            lambda i: ops.lm_head_sample(x_h, heads[i], temps, 1, 0, kws, shallow=sh, cluster=cl), nsets=2)
+    del heads
     res[f"M{M}"] = r
     print(f"M={M} done", file=sys.stderr, flush=True)
 print(json.dumps({"unit": "us per op (graph replay over 16 weight sets)", "results": res}, indent=1))

@@ -12,5 +12,6 @@ rc=$?; echo "linear tests rc=$rc" >> gpurun_out/nr_linear_tests.log
 if [ $rc -eq 0 ]; then
   timeout 900 python profiles/linear_microbench.py > gpurun_out/nr_linear_microbench.json 2> gpurun_out/nr_linear_microbench.err
   B200_LINEAR=tc timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_tc.json 2> gpurun_out/nr_bench_tc.err
+  B200_LM_HEAD=fused timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_fused_head.json 2> gpurun_out/nr_bench_fused_head.err
 fi
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_default.json 2> gpurun_out/nr_bench_default.err

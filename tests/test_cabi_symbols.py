@@ -148,5 +148,11 @@ def test_argument_validation_needs_no_gpu():
     assert lib.b200_linear(p, 128, p, p, 64, 1, 64, 128, 0, 32, 2, 0, None) == EINVAL
     assert lib.b200_linear(p, 64, p, p, 64, 1, 48, 64, 0, 32, 1, 0, None) == EUNSUPPORTED
     assert lib.b200_linear(p, 64, p, p, 64, 0, 64, 64, 0, 32, 1, 0, None) == 0
+    # staged fused LM head + sampling: hidden, head, key workspace and one of out / out_keys are required
+    assert lib.b200_lm_head_sample(None, 64, p, 1, 128, 64, None, 0, 0, 0, None, p, p, None, 128, 0, None) == EINVAL
+    assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 64, None, 0, 0, 0, None, p, None, None, 128, 0, None) == EINVAL
+    assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 72, None, 0, 0, 0, None, p, p, None, 128, 0, None) == EUNSUPPORTED
+    assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 64, None, 2 ** 32, 0, 0, None, p, p, None, 128, 0, None) == EUNSUPPORTED
+    assert lib.b200_lm_head_sample(p, 64, p, 0, 128, 64, None, 0, 0, 0, None, p, p, None, 128, 0, None) == 0
     assert lib.b200_add_rmsnorm_partials(None, 1, p, p, p, 1, 64, 1e-6, 0, None) == EINVAL
     assert lib.b200_add_rmsnorm_partials(p, 1, p, p, p, 1, 10000, 1e-6, 0, None) == EUNSUPPORTED

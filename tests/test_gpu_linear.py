@@ -178,3 +178,43 @@ def test_model_with_tc_linear_matches_library_path(preset, monkeypatch):
     for i, (g, w) in enumerate(zip(got, want)):
         rel = ((g - w).norm() / w.norm()).item()
         assert rel < 1e-2, f"step {i}: relative L2 {rel}"
+
+
+@pytest.mark.parametrize("rows", [1, 37, 256])
+@pytest.mark.parametrize("vocab,block_n,cluster", [(151936, 128, 1), (18992, 128, 1), (18992, 64, 1), (4096, 32, 2), (151936, 128, 4)])
+def test_fused_lm_head_sampling_matches_the_two_kernel_path(rows, vocab, block_n, cluster):
+    """hidden -> tokens without materialising logits, against F.linear + b200_sample on the same inputs: same RNG, same
+    scoring, so tokens can differ only where two candidates are within the bf16 rounding of differently-ordered sums."""
+    from nanovllm import ops
+    k = 1024
+    if (-(-vocab // block_n)) % cluster:
+        pytest.skip("column blocks not divisible by the cluster size")
+    x, w = _inputs(rows, vocab, k, seed=rows + vocab)
+    w = (w.float() * 8).to(torch.bfloat16)                        # logits with a spread of a few units, like a real head
+    temps = torch.tensor([0.0 if i % 3 == 0 else 0.8 for i in range(rows)], dtype=torch.float32, device="cuda")
+    ws = torch.zeros(rows, dtype=torch.int64, device="cuda")
+    offset = 7 * vocab
+    logits = x @ w.t()
+    want = ops.sample(logits, temps, seed=11, step=5, index_offset=offset)
+    keys = torch.empty(rows, dtype=torch.int64, device="cuda")
+    got = ops.lm_head_sample(x, w, temps, 11, 5, ws, index_offset=offset, out_keys=keys, out=torch.empty(rows, dtype=torch.int64, device="cuda"),
+                             block_n=block_n, cluster=cluster)
+    torch.cuda.synchronize()
+    assert int(ws.abs().max()) == 0, "the key workspace must be left empty"
+    assert ((got >= offset) & (got < offset + vocab)).all()
+    assert torch.equal(ops.tokens_from_keys(keys), got)
+    same = (got == want).float().mean().item()
+    assert same >= 0.95, f"only {same:.3f} of the rows agree with the two-kernel path"
+    lf = logits.float()
+    tol = 2 * 2.0 ** -8 * lf.abs().max().item()
+    for r in range(rows):
+        if temps[r] == 0 and got[r] != want[r]:                  # greedy disagreement only on a near-tie
+            assert (lf[r].max() - lf[r, got[r] - offset]).item() <= tol
+    # deterministic, and fresh noise for another step
+    again = ops.lm_head_sample(x, w, temps, 11, 5, ws, index_offset=offset, block_n=block_n, cluster=cluster)
+    assert torch.equal(again, got)
+    other = ops.lm_head_sample(x, w, temps, 11, 6, ws, index_offset=offset, block_n=block_n, cluster=cluster)
+    sampled = temps > 0
+    if rows >= 37:
+        assert (other[sampled] != got[sampled]).any()
+    assert torch.equal(other[~sampled], got[~sampled])
