@@ -162,6 +162,16 @@ int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t data_offset,
                                void* residual, const void* weight, void* out, int rows, int cols, float eps,
                                void* stream);
 
+/* (staged, not yet run on a GPU) The same exchange with the sum taken inside the NVSwitch (NVLS): partials are read
+ * through `multicast_base`, the multicast mapping of the same symmetric allocation, with multimem.ld_reduce (fp32
+ * accumulation in the switch, ONE rounding to bf16 -- the rounding point of the reference's bf16 all_reduce), so a
+ * rank moves `rows x cols x 2` bytes instead of world times that.  Handshake, arguments and outputs as above, except
+ * that residual <- bf16(residual + bf16(sum_p partial_p)). */
+int b200_allreduce_add_rmsnorm_nvls(const void* peer_bases_dev, const void* multicast_base, uint64_t data_offset,
+                                    uint64_t flag_offset, int* epoch, unsigned int* done, int* err_flag, int rank,
+                                    int world, void* residual, const void* weight, void* out, int rows, int cols,
+                                    float eps, void* stream);
+
 /* SiluAndMul.forward (layers/activation.py:8-11): out[r, c] = silu(x[r, c]) * x[r, inter + c]. */
 int b200_silu_mul(const void* x, void* out, int rows, int inter, void* stream);
 

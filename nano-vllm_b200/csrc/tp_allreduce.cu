@@ -31,8 +31,19 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
     return v;
 }
 
+// In-switch reduction (NVLS): one multimem load returns the sum over all ranks of the 8 bf16 at a multicast address,
+// accumulated in fp32 inside the NVSwitch and rounded to bf16 once -- the rounding point of the reference's
+// dist.all_reduce on bf16 tensors.  Every rank then moves `data` bytes over its links instead of world x data.
+__device__ __forceinline__ uint4 multimem_sum_bf16x8(const void* mc_addr) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+
+template <bool NVLS>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
-    void* const* __restrict__ bases, uint64_t data_off, uint64_t flag_off, int* epoch, unsigned int* done, int* err, int rank,
+    void* const* __restrict__ bases, const uint8_t* mc_base, uint64_t data_off, uint64_t flag_off, int* epoch, unsigned int* done, int* err, int rank,
     int world, __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* out, int cols, float eps) {
     __shared__ float red[4];
     __shared__ int s_epoch;
@@ -77,13 +88,20 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
         const int idx = threadIdx.x + k * AR_THREADS;
         if (idx < nvec) {
             unpack8(r4[idx], v[k]);                   // residual, then the partials in rank order
+            if constexpr (NVLS) {
+                float t[8];
+                unpack8(multimem_sum_bf16x8(mc_base + data_off + ((int64_t)row * nvec + idx) * 16), t);
 #pragma unroll
-            for (int p = 0; p < AR_MAX_WORLD; ++p) {
-                if (p < world) {
-                    float t[8];
-                    unpack8(__ldcv(src[p] + idx), t);
+                for (int e = 0; e < 8; ++e) v[k][e] += t[e];
+            } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[k][e] += t[e];
+                for (int p = 0; p < AR_MAX_WORLD; ++p) {
+                    if (p < world) {
+                        float t[8];
+                        unpack8(__ldcv(src[p] + idx), t);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[k][e] += t[e];
+                    }
                 }
             }
             r4[idx] = pack8(v[k]);
@@ -126,8 +144,25 @@ extern "C" int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t d
     if (world < 2 || world > AR_MAX_WORLD || rank < 0 || rank >= world) return B200_EINVAL;
     if (cols <= 0 || cols % 8 || cols > AR_THREADS * AR_MAXV * 8 || (data_offset & 15) || (flag_offset & 3)) return B200_EUNSUPPORTED;
     if (rows == 0) return B200_OK;
-    allreduce_add_rmsnorm_kernel<<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<void* const*>(peer_bases_dev), data_offset, flag_offset, epoch, done, err_flag, rank, world,
+    allreduce_add_rmsnorm_kernel<false><<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<void* const*>(peer_bases_dev), nullptr, data_offset, flag_offset, epoch, done, err_flag, rank, world,
         static_cast<__nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, eps);
+    return b200_launch_status(nullptr);
+}
+
+// Same exchange with the reduction done inside the NVSwitch (staged: not yet run on a GPU).  `multicast_base` is the
+// multicast mapping of the same symmetric allocation (torch symmetric memory: handle.multicast_ptr).
+extern "C" int b200_allreduce_add_rmsnorm_nvls(const void* peer_bases_dev, const void* multicast_base, uint64_t data_offset,
+                                               uint64_t flag_offset, int* epoch, unsigned int* done, int* err_flag, int rank,
+                                               int world, void* residual, const void* weight, void* out, int rows, int cols,
+                                               float eps, void* stream) {
+    if (!peer_bases_dev || !multicast_base || !epoch || !done || !residual || !weight || !out || rows < 0) return B200_EINVAL;
+    if (world < 2 || world > AR_MAX_WORLD || rank < 0 || rank >= world) return B200_EINVAL;
+    if (cols <= 0 || cols % 8 || cols > AR_THREADS * AR_MAXV * 8 || (data_offset & 15) || (flag_offset & 3) || ((uintptr_t)multicast_base & 15))
+        return B200_EUNSUPPORTED;
+    if (rows == 0) return B200_OK;
+    allreduce_add_rmsnorm_kernel<true><<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<void* const*>(peer_bases_dev), static_cast<const uint8_t*>(multicast_base), data_offset, flag_offset, epoch, done, err_flag,
+        rank, world, static_cast<__nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, eps);
     return b200_launch_status(nullptr);
 }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200_add_rmsnorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200_qknorm_rope_store": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp]),
     "b200_allreduce_add_rmsnorm": (_i, [_vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "b200_allreduce_add_rmsnorm_nvls": (_i, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200_silu_mul": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200_embedding": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200_gather_tokens": (_i, [_vp, _vp, _vp, _i, _vp]),

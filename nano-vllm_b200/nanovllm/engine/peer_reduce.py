@@ -31,6 +31,9 @@ class PeerReduce:
         torch.cuda.synchronize()
         self.handle = symm.rendezvous(self.raw, dist.group.WORLD)
         self.bases_dev = int(self.handle.buffer_ptrs_dev)
+        # B200_TP_ALLREDUCE=nvls (staged, opt-in): sum inside the NVSwitch through the multicast mapping, when there is one
+        self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.nvls = os.environ.get("B200_TP_ALLREDUCE", "peer") == "nvls" and self.mc_ptr != 0
         self.state = torch.zeros(3, dtype=torch.int32, device=device)           # [epoch, done counter, error flag]
         self.views = [self.raw[i * self.buf_bytes:i * self.buf_bytes + rows_cap * hidden * 2].view(torch.bfloat16).view(rows_cap, hidden)
                       for i in range(2)]
@@ -47,7 +50,7 @@ class PeerReduce:
     @classmethod
     def create(cls, rows_cap, hidden, rank, world, device):
         """The workspace, or None -- decided unanimously -- when peer memory cannot be set up or fails its self-test."""
-        if os.environ.get("B200_TP_ALLREDUCE", "peer") != "peer":
+        if os.environ.get("B200_TP_ALLREDUCE", "peer") not in ("peer", "nvls"):
             return None
         obj, why = None, ""
         try:
@@ -105,6 +108,13 @@ class PeerReduce:
         if out is None:
             out = torch.empty_like(residual)
         lib = nat.load()
+        if self.nvls:
+            nat.check(lib.b200_allreduce_add_rmsnorm_nvls(self.bases_dev, self.mc_ptr, self.turn * self.buf_bytes, self.flag_off,
+                                                          self.state.data_ptr(), self.state.data_ptr() + 4, self.state.data_ptr() + 8,
+                                                          self.rank, self.world, residual.data_ptr(), weight.data_ptr(), out.data_ptr(),
+                                                          rows, self.hidden, eps, ops._stream()))
+            self.calls += 1
+            return out, residual
         nat.check(lib.b200_allreduce_add_rmsnorm(self.bases_dev, self.turn * self.buf_bytes, self.flag_off,
                                                  self.state.data_ptr(), self.state.data_ptr() + 4, self.state.data_ptr() + 8,
                                                  self.rank, self.world, residual.data_ptr(), weight.data_ptr(), out.data_ptr(),

@@ -15,3 +15,5 @@ if [ $rc -eq 0 ]; then
   B200_LM_HEAD=fused timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_fused_head.json 2> gpurun_out/nr_bench_fused_head.err
 fi
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_default.json 2> gpurun_out/nr_bench_default.err
+# Multi-GPU legs (separate gpurun --gpus N calls; fused exchange at N=8 was never measured, NVLS variant never run):
+#   gpurun --gpus 8 --timeout 1500 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/nr_tp8_peer.json; B200_TP_ALLREDUCE=nvls python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/nr_tp8_nvls.json'
