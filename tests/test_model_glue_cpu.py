@@ -199,3 +199,50 @@ def test_staged_tc_linear_path_glue(preset, monkeypatch):
     for i, (g, w) in enumerate(zip(got, want)):
         rel = ((g.float() - w.float()).norm() / w.float().norm()).item()
         assert rel < 1e-2, f"step {i}: relative L2 {rel}"
+
+
+def test_fused_lm_head_runner_glue(monkeypatch):
+    """ModelRunner._forward_and_sample with B200_LM_HEAD=fused hands the right tensors to ops.lm_head_sample (staged path)."""
+    import nanovllm.engine.model_runner as mr
+    from nanovllm.models.qwen3 import Qwen3ForCausalLM
+    from nanovllm.utils.context import reset_context, set_context
+    seen = {}
+
+    class Ops:
+        @staticmethod
+        def lm_head_sample(hidden, lm_head, temps, seed, step, key_ws, out=None, index_offset=0, out_keys=None, step_dev=None, **kw):
+            assert hidden.dim() == 2 and hidden.shape[1] == lm_head.shape[1] and key_ws.numel() >= hidden.shape[0]
+            assert out is not None and out.shape == (hidden.shape[0],) and out.dtype == torch.int64
+            seen.update(rows=hidden.shape[0], seed=seed, step=step, step_dev=step_dev, offset=index_offset)
+            out.copy_((hidden.float() @ lm_head.float().t()).argmax(-1))
+            return out
+
+        @staticmethod
+        def sample(*a, **k):
+            raise AssertionError("the two-kernel path must not run when the fused head is on")
+
+    monkeypatch.setattr(mr, "ops", Ops)
+    hidden_all = torch.randn(10, 64).to(torch.bfloat16)
+    head = torch.randn(500, 64).to(torch.bfloat16)
+
+    class Model:
+        lm_head = head
+
+        def __call__(self, ids, pos):
+            return hidden_all
+
+        def last_token_rows(self, h):
+            return Qwen3ForCausalLM.last_token_rows(self, h)
+
+    runner = SimpleNamespace(model=Model(), fused_lm_head=True, world_size=1, sample_seed=3, vocab_offset=0,
+                             g_keyws=torch.zeros(16, dtype=torch.int64), g_tokens=torch.zeros(16, dtype=torch.int64),
+                             g_keys=torch.zeros(16, dtype=torch.int64))
+    cu = torch.tensor([0, 4, 10], dtype=torch.int32)
+    set_context(True, cu, cu, 6, 6, None, None, None)                       # prefill: the last token of each of 2 sequences
+    step_dev = torch.zeros(1, dtype=torch.int64)
+    mr.ModelRunner._forward_and_sample(runner, torch.zeros(10, dtype=torch.int64), torch.zeros(10, dtype=torch.int64),
+                                       torch.zeros(2), step_dev, 2)
+    reset_context()
+    assert seen == dict(rows=2, seed=3, step=0, step_dev=step_dev, offset=0)
+    want = (hidden_all[[3, 9]].float() @ head.float().t()).argmax(-1)
+    assert torch.equal(runner.g_tokens[:2], want)
