@@ -154,6 +154,44 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch, compiled in only with -DB200_PDL (make PDL=1 -> libb200attn_pdl.so; staged, never
+// run on a GPU).  Without the define both macros expand to exactly what the sources said before: the default
+// library's SASS is unchanged.  With it every kernel starts with launch_dependents + wait (a no-op for a launch
+// without the attribute) and every launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so inside a
+// captured step the next kernel's blocks are scheduled while the previous kernel drains.
+// ------------------------------------------------------------------------------------------
+#define B200_UNPAREN(...) __VA_ARGS__
+#ifdef B200_PDL
+#define B200_PDL_SYNC()                                                      \
+    do {                                                                     \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                   \
+    } while (0)
+template <typename... KArgs, typename... Args>
+static inline void b200_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError()
+}
+#define B200_LAUNCH(kernel_in_parens, grid, block, smem, stream, ...) \
+    b200_launch_pdl(B200_UNPAREN kernel_in_parens, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+#else
+#define B200_PDL_SYNC() \
+    do {                \
+    } while (0)
+#define B200_LAUNCH(kernel_in_parens, grid, block, smem, stream, ...) \
+    B200_UNPAREN kernel_in_parens<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 static inline int ilog2_exact(int v) {
     int s = 0;
     while ((1 << s) < v) ++s;

@@ -50,6 +50,7 @@ struct DecodeSmem {
 
 template <int G, int NWARPS, int NSTAGES, bool FUSED>
 __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const DecodeParams p) {
+    B200_PDL_SYNC();
     using L = DecodeSmem<G, NWARPS, NSTAGES, FUSED>;
     extern __shared__ __align__(128) uint8_t smem[];
     int* cum = reinterpret_cast<int*>(smem + L::kOffCum);
@@ -505,7 +506,7 @@ int launch_variant(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) 
             B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
             configured = true;
         }
-        kern<<<ctx->sm_count, NW * 32, L::kTotal, stream>>>(prm);
+        B200_LAUNCH((kern), ctx->sm_count, NW * 32, L::kTotal, stream, prm);
         return b200_launch_status(ctx);
     }
 }

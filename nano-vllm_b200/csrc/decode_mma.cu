@@ -64,6 +64,7 @@ template <int G>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 paged_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                         const DecodeParams p, const long long layer_row0) {
+    B200_PDL_SYNC();
     using L = MmaSmem<G>;
     constexpr int NWARPS = MMA_WARPS, NSTAGES = MMA_STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -375,7 +376,7 @@ int launch_mma(b200_ctx* ctx, const CUtensorMap& tk, const CUtensorMap& tv, cons
         B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         configured = true;
     }
-    kern<<<ctx->sm_count, MMA_WARPS * 32, L::kTotal, st>>>(tk, tv, prm, row0);
+    B200_LAUNCH((kern), ctx->sm_count, MMA_WARPS * 32, L::kTotal, st, tk, tv, prm, row0);
     return b200_launch_status(ctx);
 }
 

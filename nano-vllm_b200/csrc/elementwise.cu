@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ w,
                                                                __nv_bfloat16* out, int64_t out_stride, int cols,
                                                                float eps) {
+    B200_PDL_SYNC();
     __shared__ float red[4];
     const int row = blockIdx.x;
     const int nvec = cols >> 3;
@@ -74,6 +75,7 @@ template <bool HAS_RES, int NV>   // NV = uint4 per lane, cols = NV * 256
 __global__ void __launch_bounds__(128) rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride,
                                                            __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w,
                                                            __nv_bfloat16* out, int64_t out_stride, int rows, float eps) {
+    B200_PDL_SYNC();
     constexpr int cols = NV * 256;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -121,10 +123,10 @@ bool launch_rmsnorm_warp(const __nv_bfloat16* x, int64_t xs, __nv_bfloat16* res,
     if (cols % 256 || cols > 2048 || rows > 4096) return false;       // big prefill batches keep the block-per-row kernel
     const unsigned grid = (rows + 3) / 4;
     switch (cols / 256) {
-        case 1: rmsnorm_warp_kernel<HAS_RES, 1><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
-        case 2: rmsnorm_warp_kernel<HAS_RES, 2><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
-        case 4: rmsnorm_warp_kernel<HAS_RES, 4><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
-        case 8: rmsnorm_warp_kernel<HAS_RES, 8><<<grid, 128, 0, st>>>(x, xs, res, w, out, os, rows, eps); return true;
+        case 1: B200_LAUNCH((rmsnorm_warp_kernel<HAS_RES, 1>), grid, 128, 0, st, x, xs, res, w, out, os, rows, eps); return true;
+        case 2: B200_LAUNCH((rmsnorm_warp_kernel<HAS_RES, 2>), grid, 128, 0, st, x, xs, res, w, out, os, rows, eps); return true;
+        case 4: B200_LAUNCH((rmsnorm_warp_kernel<HAS_RES, 4>), grid, 128, 0, st, x, xs, res, w, out, os, rows, eps); return true;
+        case 8: B200_LAUNCH((rmsnorm_warp_kernel<HAS_RES, 8>), grid, 128, 0, st, x, xs, res, w, out, os, rows, eps); return true;
         default: return false;
     }
 }
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(128) qknorm_rope_store_kernel(
     const __nv_bfloat16* __restrict__ qw, const __nv_bfloat16* __restrict__ kw,
     const float* __restrict__ cos_sin, float eps, const int32_t* __restrict__ slot_mapping,
     __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int block_shift, int n) {
+    B200_PDL_SYNC();
     const int heads = hq + 2 * hkv;
     const int64_t unit = ((int64_t)blockIdx.x * 128 + threadIdx.x) >> 4;        // (token, head) index
     const int j = threadIdx.x & 15;
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(128) store_kv_kernel(const __nv_bfloat16* __re
                                                        const int32_t* __restrict__ slot_mapping,
                                                        __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int hkv,
                                                        int block_shift, int n) {
+    B200_PDL_SYNC();
     const int64_t gwarp = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (gwarp >= (int64_t)n * hkv) return;
     const int tok = (int)(gwarp / hkv);
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(128) store_kv_kernel(const __nv_bfloat16* __re
 // SiluAndMul.forward (layers/activation.py:8-11)
 __global__ void __launch_bounds__(256) silu_mul_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* out,
                                                        int64_t total_vec, int inter_vec) {
+    B200_PDL_SYNC();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / inter_vec;
         const int col = (int)(i - row * inter_vec);
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(128) embedding_kernel(const int64_t* __restrict__ ids,
                                                         const __nv_bfloat16* __restrict__ table,
                                                         __nv_bfloat16* out, int hidden_vec) {
+    B200_PDL_SYNC();
     const int tok = blockIdx.x;
     const uint4* src = reinterpret_cast<const uint4*>(table) + ids[tok] * hidden_vec;
     uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)tok * hidden_vec;
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(128) embedding_kernel(const int64_t* __restric
 }
 
 __global__ void gather_tokens_kernel(int64_t* ids, const int32_t* __restrict__ src, const int64_t* __restrict__ prev, int n) {
+    B200_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const int s = src[i];
@@ -263,7 +270,7 @@ extern "C" int b200_rmsnorm(const void* x, int64_t x_stride0, const void* weight
     if (launch_rmsnorm_warp<false>(static_cast<const __nv_bfloat16*>(x), x_stride0, nullptr, static_cast<const __nv_bfloat16*>(weight),
                                    static_cast<__nv_bfloat16*>(out), out_stride0, rows, cols, eps, static_cast<cudaStream_t>(stream)))
         return b200_launch_status(nullptr);
-    rmsnorm_kernel<false><<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((rmsnorm_kernel<false>), rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(x), x_stride0, nullptr, static_cast<const __nv_bfloat16*>(weight),
         static_cast<__nv_bfloat16*>(out), out_stride0, cols, eps);
     return b200_launch_status(nullptr);
@@ -279,7 +286,7 @@ extern "C" int b200_add_rmsnorm(const void* x, void* residual, const void* weigh
                                   static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, rows, cols, eps,
                                   static_cast<cudaStream_t>(stream)))
         return b200_launch_status(nullptr);
-    rmsnorm_kernel<true><<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((rmsnorm_kernel<true>), rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(x), cols, static_cast<__nv_bfloat16*>(residual),
         static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, cols, eps);
     return b200_launch_status(nullptr);
@@ -303,7 +310,7 @@ extern "C" int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64
     }
     const int64_t units = (int64_t)n * (num_q_heads + 2 * num_kv_heads);       // one half-warp each, 8 per block
     const unsigned blocks = (unsigned)((units + 7) / 8);
-    qknorm_rope_store_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((qknorm_rope_store_kernel), blocks, 128, 0, static_cast<cudaStream_t>(stream), 
         static_cast<__nv_bfloat16*>(qkv), qkv_stride0, num_q_heads, num_kv_heads, positions,
         static_cast<const __nv_bfloat16*>(q_norm_weight), static_cast<const __nv_bfloat16*>(k_norm_weight),
         cos_sin, eps, slot_mapping, kc, vc, shift, n);
@@ -319,7 +326,7 @@ extern "C" int b200_store_kv(b200_ctx* ctx, int layer, const void* k, int64_t k_
     if (k_stride0 % 4 || v_stride0 % 4 || ((uintptr_t)k & 7) || ((uintptr_t)v & 7)) return B200_EINVAL;
     if (n == 0) return B200_OK;
     const int64_t warps = (int64_t)n * ctx->num_kv_heads;
-    store_kv_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((store_kv_kernel), (unsigned)((warps + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(k), k_stride0, static_cast<const __nv_bfloat16*>(v), v_stride0,
         slot_mapping, ctx->k_layer(layer), ctx->v_layer(layer), ctx->num_kv_heads, ctx->block_shift, n);
     return b200_launch_status(ctx);
@@ -332,7 +339,7 @@ extern "C" int b200_silu_mul(const void* x, void* out, int rows, int inter, void
     const int64_t total = (int64_t)rows * (inter / 8);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    silu_mul_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((silu_mul_kernel), (unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), total, inter / 8);
     return b200_launch_status(nullptr);
 }
@@ -342,7 +349,7 @@ extern "C" int b200_embedding(const int64_t* ids, const void* table, void* out, 
     if (!ids || !table || !out || n < 0) return B200_EINVAL;
     if (hidden <= 0 || hidden % 8 || !aligned16(table) || !aligned16(out)) return B200_EINVAL;
     if (n == 0) return B200_OK;
-    embedding_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((embedding_kernel), n, 128, 0, static_cast<cudaStream_t>(stream), 
         ids, static_cast<const __nv_bfloat16*>(table), static_cast<__nv_bfloat16*>(out), hidden / 8);
     return b200_launch_status(nullptr);
 }
@@ -350,6 +357,6 @@ extern "C" int b200_embedding(const int64_t* ids, const void* table, void* out, 
 extern "C" int b200_gather_tokens(int64_t* ids, const int32_t* src, const int64_t* prev_tokens, int n, void* stream) {
     if (!ids || !src || !prev_tokens || n < 0) return B200_EINVAL;
     if (n == 0) return B200_OK;
-    gather_tokens_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, src, prev_tokens, n);
+    B200_LAUNCH((gather_tokens_kernel), (n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), ids, src, prev_tokens, n);
     return b200_launch_status(nullptr);
 }

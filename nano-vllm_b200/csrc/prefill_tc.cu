@@ -59,6 +59,7 @@ constexpr uint32_t IDESC_PV = make_idesc(BM, D, true);
 __global__ void __launch_bounds__(TC_THREADS, 2)
 prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const TcParams p) {
+    B200_PDL_SYNC();
     extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte swizzle atoms need 1024-byte alignment
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) __trap();
@@ -302,6 +303,6 @@ int b200_prefill_tc_launch(b200_ctx* ctx, int layer, const void* q, int64_t q_st
     }
     dim3 grid((max_seqlen_q + BM - 1) / BM, num_q_heads, num_seqs);
     if (grid.z > 65535 || grid.y > 65535) return B200_EUNSUPPORTED;
-    prefill_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, prm);
+    B200_LAUNCH((prefill_tc_kernel), grid, TC_THREADS, TC_SMEM, stream, tq, tk, tv, prm);
     return b200_launch_status(ctx);
 }

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const void* __re
                                                                 int64_t index_offset, uint64_t seed, uint64_t step,
                                                                 const int64_t* __restrict__ step_dev,
                                                                 int64_t* out, int64_t* out_keys, int splits) {
+    B200_PDL_SYNC();
     const int row = blockIdx.x;
     const int split = blockIdx.y;
     const float t = temperatures ? temperatures[row] : 0.f;
@@ -118,10 +119,10 @@ extern "C" int b200_sample(const void* logits, int logits_is_fp32, int64_t logit
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid(rows, splits);
     if (logits_is_fp32) {
-        sample_kernel<true><<<grid, SAMPLE_THREADS, 0, st>>>(logits, logits_stride0, temperatures, vocab, index_offset, seed, step, step_dev, out, out_keys, splits);
+        B200_LAUNCH((sample_kernel<true>), grid, SAMPLE_THREADS, 0, st, logits, logits_stride0, temperatures, vocab, index_offset, seed, step, step_dev, out, out_keys, splits);
     } else {
         if (((uintptr_t)logits & 15) || (logits_stride0 % 8)) return B200_EINVAL;
-        sample_kernel<false><<<grid, SAMPLE_THREADS, 0, st>>>(logits, logits_stride0, temperatures, vocab, index_offset, seed, step, step_dev, out, out_keys, splits);
+        B200_LAUNCH((sample_kernel<false>), grid, SAMPLE_THREADS, 0, st, logits, logits_stride0, temperatures, vocab, index_offset, seed, step, step_dev, out, out_keys, splits);
     }
     return b200_launch_status(nullptr);
 }

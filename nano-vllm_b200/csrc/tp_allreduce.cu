@@ -45,6 +45,7 @@ template <bool NVLS>
 __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
     void* const* __restrict__ bases, const uint8_t* mc_base, uint64_t data_off, uint64_t flag_off, int* epoch, unsigned int* done, int* err, int rank,
     int world, __nv_bfloat16* residual, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* out, int cols, float eps) {
+    B200_PDL_SYNC();
     __shared__ float red[4];
     __shared__ int s_epoch;
     const int row = blockIdx.x;
@@ -144,7 +145,7 @@ extern "C" int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t d
     if (world < 2 || world > AR_MAX_WORLD || rank < 0 || rank >= world) return B200_EINVAL;
     if (cols <= 0 || cols % 8 || cols > AR_THREADS * AR_MAXV * 8 || (data_offset & 15) || (flag_offset & 3)) return B200_EUNSUPPORTED;
     if (rows == 0) return B200_OK;
-    allreduce_add_rmsnorm_kernel<false><<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((allreduce_add_rmsnorm_kernel<false>), rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<void* const*>(peer_bases_dev), nullptr, data_offset, flag_offset, epoch, done, err_flag, rank, world,
         static_cast<__nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, eps);
     return b200_launch_status(nullptr);
@@ -161,7 +162,7 @@ extern "C" int b200_allreduce_add_rmsnorm_nvls(const void* peer_bases_dev, const
     if (cols <= 0 || cols % 8 || cols > AR_THREADS * AR_MAXV * 8 || (data_offset & 15) || (flag_offset & 3) || ((uintptr_t)multicast_base & 15))
         return B200_EUNSUPPORTED;
     if (rows == 0) return B200_OK;
-    allreduce_add_rmsnorm_kernel<true><<<rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+    B200_LAUNCH((allreduce_add_rmsnorm_kernel<true>), rows, AR_THREADS, 0, static_cast<cudaStream_t>(stream), 
         static_cast<void* const*>(peer_bases_dev), static_cast<const uint8_t*>(multicast_base), data_offset, flag_offset, epoch, done, err_flag,
         rank, world, static_cast<__nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), cols, eps);
     return b200_launch_status(nullptr);

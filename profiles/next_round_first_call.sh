@@ -15,5 +15,10 @@ if [ $rc -eq 0 ]; then
   B200_LM_HEAD=fused timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_fused_head.json 2> gpurun_out/nr_bench_fused_head.err
 fi
 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_default.json 2> gpurun_out/nr_bench_default.err
+# 3. the PDL flavour of the library (every kernel: launch_dependents + wait, every launch with the PDL attribute)
+PDL_LIB=$PWD/nano-vllm_b200/lib/libb200attn_pdl.so
+B200ATTN_LIB=$PDL_LIB timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/nr_gpu_tests_pdl.log 2>&1; echo "pdl tests rc=$?" >> gpurun_out/nr_gpu_tests_pdl.log
+B200ATTN_LIB=$PDL_LIB timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_pdl.json 2> gpurun_out/nr_bench_pdl.err
+B200ATTN_LIB=$PDL_LIB B200_LINEAR=tc B200_LINEAR_CFG=32,32,64,8,64,8,1 timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/nr_bench_pdl_tc.json 2> gpurun_out/nr_bench_pdl_tc.err
 # Multi-GPU legs (separate gpurun --gpus N calls; fused exchange at N=8 was never measured, NVLS variant never run):
 #   gpurun --gpus 8 --timeout 1500 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/nr_tp8_peer.json; B200_TP_ALLREDUCE=nvls python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/nr_tp8_nvls.json'
