@@ -163,10 +163,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // ------------------------------------------------------------------------------------------
 #define B200_UNPAREN(...) __VA_ARGS__
 #ifdef B200_PDL
-#define B200_PDL_SYNC()                                                      \
-    do {                                                                     \
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      \
-        asm volatile("griddepcontrol.wait;" ::: "memory");                   \
+#define B200_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define B200_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define B200_PDL_SYNC()     \
+    do {                    \
+        B200_PDL_TRIGGER(); \
+        B200_PDL_WAIT();    \
     } while (0)
 template <typename... KArgs, typename... Args>
 static inline void b200_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -185,6 +187,12 @@ static inline void b200_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
 #define B200_LAUNCH(kernel_in_parens, grid, block, smem, stream, ...) \
     b200_launch_pdl(B200_UNPAREN kernel_in_parens, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
 #else
+#define B200_PDL_TRIGGER() \
+    do {                   \
+    } while (0)
+#define B200_PDL_WAIT() \
+    do {                \
+    } while (0)
 #define B200_PDL_SYNC() \
     do {                \
     } while (0)

@@ -50,7 +50,7 @@ struct DecodeSmem {
 
 template <int G, int NWARPS, int NSTAGES, bool FUSED>
 __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const DecodeParams p) {
-    B200_PDL_SYNC();
+    B200_PDL_TRIGGER();
     using L = DecodeSmem<G, NWARPS, NSTAGES, FUSED>;
     extern __shared__ __align__(128) uint8_t smem[];
     int* cum = reinterpret_cast<int*>(smem + L::kOffCum);
@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) paged_decode_kernel(const Deco
         __syncthreads();
     }
 
+    // everything above read only step metadata uploaded by the host before the first kernel of the step; q, the KV
+    // pages written by this step and the output buffer belong to the previous kernels: wait for them here (PDL flavour)
+    B200_PDL_WAIT();
     // ---- rows without context (CUDA-graph padding) produce zeros --------------------------------
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {
         if (ctxs[b] == 0) {

@@ -64,7 +64,7 @@ template <int G>
 __global__ void __launch_bounds__(MMA_WARPS * 32, 1)
 paged_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                         const DecodeParams p, const long long layer_row0) {
-    B200_PDL_SYNC();
+    B200_PDL_TRIGGER();
     using L = MmaSmem<G>;
     constexpr int NWARPS = MMA_WARPS, NSTAGES = MMA_STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -132,6 +132,9 @@ paged_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_c
         __syncthreads();
     }
 
+    // everything above read only step metadata uploaded by the host before the first kernel of the step; q, the KV
+    // pages written by this step and the output buffer belong to the previous kernels: wait for them here (PDL flavour)
+    B200_PDL_WAIT();
     for (int b = blockIdx.x; b < batch; b += gridDim.x) {     // graph-padding rows produce zeros
         if (ctxs[b] == 0) {
             const int n16 = hkv * G * (B200_HEAD_DIM / 8);
