@@ -465,8 +465,9 @@ extern "C" int b200_lm_head_sample(const void* hidden, int64_t hidden_stride0, c
     if (rows == 0) return B200_OK;
     const int cluster = 1 << ((flags >> 2) & 3);
     if (cluster > 4 || (cluster > 1 && (flags & 2))) return B200_EUNSUPPORTED;
+    if (block_n <= 0) return B200_EUNSUPPORTED;
     const int n_tiles = (vocab + block_n - 1) / block_n;
-    if (block_n <= 0 || n_tiles % cluster) return B200_EUNSUPPORTED;
+    if (n_tiles % cluster) return B200_EUNSUPPORTED;
     CUtensorMap tx, tw;
     if (!cached_map(&tx, hidden, (uint64_t)k, (uint64_t)rows, (uint64_t)hidden_stride0, LM / cluster)) return B200_EUNSUPPORTED;
     if (!cached_map(&tw, lm_head, (uint64_t)k, (uint64_t)vocab, (uint64_t)k, (uint32_t)block_n)) return B200_EUNSUPPORTED;

@@ -168,5 +168,6 @@ def test_argument_validation_needs_no_gpu():
     assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 72, None, 0, 0, 0, None, p, p, None, 128, 0, None) == EUNSUPPORTED
     assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 64, None, 2 ** 32, 0, 0, None, p, p, None, 128, 0, None) == EUNSUPPORTED
     assert lib.b200_lm_head_sample(p, 64, p, 0, 128, 64, None, 0, 0, 0, None, p, p, None, 128, 0, None) == 0
+    assert lib.b200_lm_head_sample(p, 64, p, 1, 128, 64, None, 0, 0, 0, None, p, p, None, 0, 0, None) == EUNSUPPORTED
     assert lib.b200_add_rmsnorm_partials(None, 1, p, p, p, 1, 64, 1e-6, 0, None) == EINVAL
     assert lib.b200_add_rmsnorm_partials(p, 1, p, p, p, 1, 10000, 1e-6, 0, None) == EUNSUPPORTED
