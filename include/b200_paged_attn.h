@@ -175,8 +175,10 @@ int b200_allreduce_add_rmsnorm_nvls(const void* peer_bases_dev, const void* mult
 /* SiluAndMul.forward (layers/activation.py:8-11): out[r, c] = silu(x[r, c]) * x[r, inter + c]. */
 int b200_silu_mul(const void* x, void* out, int rows, int inter, void* stream);
 
-/* F.embedding of VocabParallelEmbedding.forward (layers/embed_head.py:34-42), single shard. */
-int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden,
+/* F.embedding of VocabParallelEmbedding.forward (layers/embed_head.py:34-42), single shard.  `vocab` = rows of
+ * `table`; an id outside [0, vocab) never reads outside the table: its output row is zeros (the reference's
+ * F.embedding device-asserts there; callers validate ids on the host). */
+int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden, int64_t vocab,
                    void* stream);
 
 /* Feeds a decode step's input_ids straight from the previous step's sampled tokens, on the device:

@@ -1,7 +1,7 @@
 // Context lifetime and KV binding behind include/b200_paged_attn.h.
 #include "common.cuh"
 
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
 
 extern "C" const char* b200_strerror(int code) {
     switch (code) {
@@ -36,7 +36,7 @@ extern "C" int b200_init(int device, b200_ctx** out) {
 extern "C" void b200_destroy(b200_ctx* ctx) { delete ctx; }
 
 extern "C" const char* b200_last_cuda_error(b200_ctx* ctx) {
-    return ctx ? ctx->last_cuda_error.c_str() : "";
+    return ctx ? ctx->last_cuda_error.c_str() : b200_tls_cuda_error().c_str();   // NULL: this thread's context-less calls
 }
 
 extern "C" int b200_sm_count(const b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }

@@ -41,14 +41,41 @@ struct b200_ctx {
         }                                                             \
     } while (0)
 
+// Text of the last CUDA error seen by an entry point that has no b200_ctx (b200_rmsnorm, b200_linear, ...): kept per
+// host thread and returned by b200_last_cuda_error(NULL).
+inline std::string& b200_tls_cuda_error() {
+    static thread_local std::string text;
+    return text;
+}
+
 static inline int b200_launch_status(b200_ctx* ctx) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         if (ctx) ctx->last_cuda_error = cudaGetErrorString(e);
+        else b200_tls_cuda_error() = cudaGetErrorString(e);
         return B200_ECUDA;
     }
     return B200_OK;
 }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember the opt-in per device
+// ordinal, so that a process that drives several GPUs configures each of them (a process-wide flag would leave the second
+// device without the opt-in and its launches would fail).
+constexpr int B200_MAX_DEVICES = 64;
+struct B200SmemOptIn {
+    bool done[B200_MAX_DEVICES] = {};
+    template <typename K>
+    cudaError_t ensure(K kernel, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= B200_MAX_DEVICES) return cudaErrorInvalidDevice;
+        if (done[dev]) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) done[dev] = true;
+        return e;
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // bf16 <-> fp32 on packed words.  A bf16 is the high half of an fp32, so unpacking is one

@@ -504,11 +504,8 @@ int launch_variant(b200_ctx* ctx, const DecodeParams& prm, cudaStream_t stream) 
         return B200_EUNSUPPORTED;
     } else {
         auto kern = paged_decode_kernel<G, NW, NS, FUSED>;
-        static bool configured = false;
-        if (!configured) {
-            B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-            configured = true;
-        }
+        static B200SmemOptIn optin;
+        B200_CUDA_CHECK(ctx, optin.ensure(kern, L::kTotal));
         B200_LAUNCH((kern), ctx->sm_count, NW * 32, L::kTotal, stream, prm);
         return b200_launch_status(ctx);
     }

@@ -374,11 +374,8 @@ int launch_mma(b200_ctx* ctx, const CUtensorMap& tk, const CUtensorMap& tv, cons
     using L = MmaSmem<G>;
     static_assert(L::kTotal <= 227 * 1024, "decode (mma) shared memory exceeds the sm_100 opt-in limit");
     auto kern = paged_decode_mma_kernel<G>;
-    static bool configured = false;
-    if (!configured) {
-        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
-    }
+    static B200SmemOptIn optin;
+    B200_CUDA_CHECK(ctx, optin.ensure(kern, L::kTotal));
     B200_LAUNCH((kern), ctx->sm_count, MMA_WARPS * 32, L::kTotal, st, tk, tv, prm, row0);
     return b200_launch_status(ctx);
 }

@@ -240,11 +240,16 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const __nv_bfloat16* __re
 // F.embedding (layers/embed_head.py:38)
 __global__ void __launch_bounds__(128) embedding_kernel(const int64_t* __restrict__ ids,
                                                         const __nv_bfloat16* __restrict__ table,
-                                                        __nv_bfloat16* out, int hidden_vec) {
+                                                        __nv_bfloat16* out, int hidden_vec, int64_t vocab) {
     B200_PDL_SYNC();
     const int tok = blockIdx.x;
-    const uint4* src = reinterpret_cast<const uint4*>(table) + ids[tok] * hidden_vec;
+    const int64_t id = ids[tok];
     uint4* dst = reinterpret_cast<uint4*>(out) + (int64_t)tok * hidden_vec;
+    if (id < 0 || id >= vocab) {          // never read outside the table: an id that is not a token embeds to zeros
+        for (int i = threadIdx.x; i < hidden_vec; i += 128) dst[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(table) + id * hidden_vec;
     for (int i = threadIdx.x; i < hidden_vec; i += 128) dst[i] = src[i];
 }
 
@@ -344,13 +349,13 @@ extern "C" int b200_silu_mul(const void* x, void* out, int rows, int inter, void
     return b200_launch_status(nullptr);
 }
 
-extern "C" int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden,
+extern "C" int b200_embedding(const int64_t* ids, const void* table, void* out, int n, int hidden, int64_t vocab,
                               void* stream) {
-    if (!ids || !table || !out || n < 0) return B200_EINVAL;
+    if (!ids || !table || !out || n < 0 || vocab <= 0) return B200_EINVAL;
     if (hidden <= 0 || hidden % 8 || !aligned16(table) || !aligned16(out)) return B200_EINVAL;
     if (n == 0) return B200_OK;
     B200_LAUNCH((embedding_kernel), n, 128, 0, static_cast<cudaStream_t>(stream), 
-        ids, static_cast<const __nv_bfloat16*>(table), static_cast<__nv_bfloat16*>(out), hidden / 8);
+        ids, static_cast<const __nv_bfloat16*>(table), static_cast<__nv_bfloat16*>(out), hidden / 8, vocab);
     return b200_launch_status(nullptr);
 }
 

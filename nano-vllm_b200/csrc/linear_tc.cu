@@ -368,10 +368,10 @@ bool cached_map(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows
 template <int BN, int EPI, bool DEEP, int CL>
 int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
     using C = Cfg<BN, DEEP>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(linear_tc_kernel<BN, EPI, DEEP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return B200_ECUDA;
-        configured = true;
+    static B200SmemOptIn optin;
+    if (cudaError_t e = optin.ensure(linear_tc_kernel<BN, EPI, DEEP, CL>, C::SMEM); e != cudaSuccess) {
+        b200_tls_cuda_error() = cudaGetErrorString(e);
+        return B200_ECUDA;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

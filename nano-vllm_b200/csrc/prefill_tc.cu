@@ -216,6 +216,18 @@ prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
             *reinterpret_cast<uint4*>(prow + ((c8 ^ (tid & 7)) << 4)) = pack8(pv);
         }
+        if (j * BN + BN > len_k) {
+            // Tail block: V rows at keys >= len_k are not this sequence's (stale page rows, the next sequence of a packed
+            // batch, anything -- possibly NaN/Inf).  Their P is exactly 0, but 0 * NaN would poison the accumulator, so
+            // zero those rows of the staged tile.  A whole 128-byte row is zeroed, which is swizzle-agnostic.
+            mbar_wait(bar_v0 + b * 8, (j >> 1) & 1);
+            const int first = len_k - j * BN;                               // 1..63
+            uint8_t* vtile = base_ptr + OFF_V + b * KV_BYTES;
+            for (int i = tid; i < (BN - first) * 16; i += TC_THREADS) {     // 16 chunks of 16 B per row: 2 halves x 8
+                const int r = first + (i >> 4), c = i & 15;
+                *reinterpret_cast<uint4*>(vtile + (c >> 3) * KV_HALF + r * 128 + ((c & 7) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
         tc_fence_before();
         __syncthreads();
@@ -296,11 +308,8 @@ int b200_prefill_tc_launch(b200_ctx* ctx, int layer, const void* q, int64_t q_st
             !make_map(&tv, v, (uint64_t)num_kv_heads * D, (uint64_t)total_k, (uint64_t)v_stride0, BN))
             return B200_EUNSUPPORTED;
     }
-    static bool configured = false;
-    if (!configured) {
-        B200_CUDA_CHECK(ctx, cudaFuncSetAttribute(prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-        configured = true;
-    }
+    static B200SmemOptIn optin;
+    B200_CUDA_CHECK(ctx, optin.ensure(prefill_tc_kernel, TC_SMEM));
     dim3 grid((max_seqlen_q + BM - 1) / BM, num_q_heads, num_seqs);
     if (grid.z > 65535 || grid.y > 65535) return B200_EUNSUPPORTED;
     B200_LAUNCH((prefill_tc_kernel), grid, TC_THREADS, TC_SMEM, stream, tq, tk, tv, prm);

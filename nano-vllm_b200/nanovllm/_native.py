@@ -33,7 +33,7 @@ SIGNATURES = {
     "b200_allreduce_add_rmsnorm": (_i, [_vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200_allreduce_add_rmsnorm_nvls": (_i, [_vp, _vp, _u64, _u64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200_silu_mul": (_i, [_vp, _vp, _i, _i, _vp]),
-    "b200_embedding": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b200_embedding": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "b200_gather_tokens": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b200_sample": (_i, [_vp, _i, _i64, _vp, _i, _i, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     # staged for the next round (csrc/linear_tc.cu): exported, never run on a GPU yet, not used by the engine
@@ -77,7 +77,7 @@ def check(code: int, ctx=None):
         return
     lib = load()
     msg = lib.b200_strerror(code).decode()
-    if code == -3 and ctx is not None:
+    if code == -3:                        # ctx None: the text of this thread's last context-less call
         msg += ": " + lib.b200_last_cuda_error(ctx).decode()
     raise B200Error(f"libb200attn: {msg} (code {code})")
 

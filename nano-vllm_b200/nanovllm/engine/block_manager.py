@@ -148,3 +148,11 @@ class BlockManager:
             h = self.compute_hash(toks, h)
             self._hash[bid], self._tokens[bid] = h, tuple(toks)
             self.hash_to_block_id[h] = bid
+
+    # ---- recovery ----------------------------------------------------------------------------------
+    def forget_prefix_cache(self) -> None:
+        """Drop every hash -> block entry (the KV bytes behind them can no longer be trusted, e.g. after a failed
+        tensor-parallel exchange wrote undefined data).  Live block tables and ref counts are untouched."""
+        self.hash_to_block_id.clear()
+        for bid in range(self.num_blocks):
+            self._hash[bid], self._tokens[bid] = -1, None

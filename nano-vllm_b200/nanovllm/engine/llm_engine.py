@@ -47,12 +47,18 @@ class LLMEngine:
         Sequence.block_size = config.kvcache_block_size
         tp = config.tensor_parallel_size
         self.rank, self._procs, self._mirrors = 0, [], False
+        saved_env = None
         if tp > 1:
             if int(os.environ.get("WORLD_SIZE", "1")) == tp and "RANK" in os.environ:
                 self.rank = int(os.environ["RANK"])                                  # launcher-provided replicas
             else:
+                # spawn mode: the rendezvous variables are set only while the ranks are being constructed and are put
+                # back afterwards, so that a later LLM(...) in this process (or any child it starts) does not mistake
+                # them for a launcher's and the launcher-vs-spawn decision above stays a function of the user's env
                 import torch.multiprocessing as mp
                 port = _free_port()
+                keys = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")
+                saved_env = {k: os.environ.get(k) for k in keys}
                 os.environ.update(RANK="0", LOCAL_RANK="0", WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1",
                                   MASTER_PORT=str(port))
                 ctx = mp.get_context("spawn")
@@ -61,7 +67,15 @@ class LLMEngine:
                     p.start()
                     self._procs.append(p)
                 self._mirrors = True
-        self.model_runner = ModelRunner(config, self.rank, None)
+        try:
+            self.model_runner = ModelRunner(config, self.rank, None)
+        finally:
+            if saved_env is not None:
+                for k, v in saved_env.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
         from transformers import AutoTokenizer
         self.tokenizer = AutoTokenizer.from_pretrained(config.model, use_fast=True)
         config.eos = self.tokenizer.eos_token_id if self.tokenizer.eos_token_id is not None else -1
@@ -112,6 +126,14 @@ class LLMEngine:
         self._add_request(prompt, sampling_params)
 
     def _add_request(self, prompt: list[int], sampling_params: SamplingParams):
+        # the embedding gather indexes the table with these ids: refuse anything that is not a token of this model
+        # (the reference's F.embedding device-asserts instead, embed_head.py:38)
+        vocab = self.config.hf_config.vocab_size
+        if len(prompt) == 0:
+            raise ValueError("empty prompt")
+        lo, hi = min(prompt), max(prompt)
+        if lo < 0 or hi >= vocab:
+            raise ValueError(f"prompt token id {lo if lo < 0 else hi} is outside the vocabulary [0, {vocab})")
         self.scheduler.add(Sequence(prompt, sampling_params))
 
     def step(self):
@@ -159,10 +181,19 @@ class LLMEngine:
                 pbar.set_postfix({"Prefill": f"{int(stats['prefill'])}tok/s", "Decode": f"{int(stats['decode'])}tok/s"})
                 pbar.update(len(finished))
 
-        self._run_overlapped(on_step)
-        if pbar is not None:
-            pbar.close()
-        self.model_runner.check_peer_exchange()
+        try:
+            self._run_overlapped(on_step)
+            self.model_runner.check_peer_exchange()
+        except Exception:
+            # a step failed (e.g. the tensor-parallel exchange timed out and produced undefined data): nothing that step
+            # or its successors wrote may survive -- drop in-flight steps, retire every sequence, forget the prefix
+            # cache -- and let the error reach the caller
+            self.model_runner.call("drain")
+            self.scheduler.abort_all()
+            raise
+        finally:
+            if pbar is not None:
+                pbar.close()
         return [done[k] for k in sorted(done)]
 
     def _run_overlapped(self, on_step) -> None:

@@ -66,7 +66,7 @@ class _Staging:
 
 
 class ModelRunner:
-    def __init__(self, config: Config, rank: int = 0, event=None, sample_seed: int = 0):
+    def __init__(self, config: Config, rank: int = 0, event=None, sample_seed: int | None = None):
         self.config = config
         hf = config.hf_config
         self.block_size = config.kvcache_block_size
@@ -82,18 +82,38 @@ class ModelRunner:
         if not torch.cuda.is_available():
             raise nat.B200Error("ModelRunner needs a CUDA device: the B200 path has no CPU fallback")
         local = int(os.environ.get("LOCAL_RANK", rank))
+        # Debug / CI knob: B200_TP_BACKEND=gloo with B200_TP_ONE_DEVICE=1 runs all tensor-parallel ranks on ONE GPU
+        # (time-sliced processes, collectives through gloo, eager only): the sharding, the vocab-parallel sampling and
+        # the SPMD engine can then be checked on a single-GPU box.  Never the fast path: NCCL is the default.
+        backend = os.environ.get("B200_TP_BACKEND", "nccl")
+        if os.environ.get("B200_TP_ONE_DEVICE") == "1":
+            local = 0
         torch.cuda.set_device(local)
         self.device = torch.device("cuda", local)
         self._own_pg = False
         if self.world_size > 1 and not dist.is_initialized():
             addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
             port = os.environ.get("MASTER_PORT", "2333")
-            dist.init_process_group("nccl", init_method=f"tcp://{addr}:{port}", world_size=self.world_size,
-                                    rank=rank, device_id=self.device)
+            kw = dict(device_id=self.device) if backend == "nccl" else {}
+            dist.init_process_group(backend, init_method=f"tcp://{addr}:{port}", world_size=self.world_size, rank=rank, **kw)
             self._own_pg = True
+        if self.world_size > 1 and dist.get_backend() != "nccl" and not config.enforce_eager:
+            raise ValueError("CUDA graphs need the NCCL backend (gloo collectives cannot be captured): pass enforce_eager=True")
         if self.world_size > 1:
             assert dist.get_world_size() == self.world_size, "tensor_parallel_size must equal the process-group size"
         self.native = nat.handle(local)
+        # Sampling randomness: a fresh 63-bit seed per engine unless one is given (B200_SAMPLE_SEED or the argument);
+        # every tensor-parallel rank must use the same one (each scores its own vocabulary shard with the RNG keyed by
+        # the global token id), so rank 0's choice is broadcast.
+        if sample_seed is None and os.environ.get("B200_SAMPLE_SEED"):
+            sample_seed = int(os.environ["B200_SAMPLE_SEED"])
+        if sample_seed is None:
+            sample_seed = int.from_bytes(os.urandom(8), "little") >> 1
+        if self.world_size > 1:
+            t = torch.tensor([sample_seed], dtype=torch.int64, device=self.device)
+            dist.broadcast(t, src=0)
+            sample_seed = int(t.item())
+        self.sample_seed = sample_seed
 
         self.model = Qwen3ForCausalLM(hf, rank, self.world_size, self.device, max_position=hf.max_position_embeddings)
         load_model(self.model, config.model, allow_random=bool(os.environ.get("NANOVLLM_ALLOW_RANDOM_INIT")))
@@ -180,6 +200,7 @@ class ModelRunner:
         self.g_keyws = torch.zeros(S, dtype=torch.int64, device="cuda")      # running-max keys of the fused LM head (zero between steps)
         self.fused_lm_head = os.environ.get("B200_LM_HEAD", "gemm") == "fused"
         self.h_tokens = [torch.empty(S, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+        self.h_err = [torch.zeros(1, dtype=torch.int32, pin_memory=True) for _ in range(2)]   # peer-exchange error flag per step
         self.h_tokens_np = [t.numpy() for t in self.h_tokens]
         self.h2d_bytes_last = 0
         self.d2h_bytes_last = 0
@@ -434,6 +455,9 @@ class ModelRunner:
         self._launches += 1
         assert len(self._pending) < 2, "at most two steps in flight"
         self.h_tokens[kk][:n].copy_(self.g_tokens[:n], non_blocking=True)
+        peer = getattr(self.model, "peer", None)
+        if peer is not None:              # the exchange kernel's timeout flag rides along with the tokens: checked every step
+            self.h_err[kk].copy_(peer.state[2:3], non_blocking=True)
         self._done[kk].record()
         self._pending.append((kk, n))
         self.d2h_bytes_last = n * 8
@@ -443,7 +467,16 @@ class ModelRunner:
         """Wait for the oldest step enqueued by launch() (that step's only host sync) and return its token ids."""
         kk, n = self._pending.popleft()
         self._done[kk].synchronize()
+        if int(self.h_err[kk][0]) != 0:
+            from .peer_reduce import PeerExchangeTimeout
+            raise PeerExchangeTimeout("tensor-parallel peer exchange timed out in this step (a rank stopped or fell >10 s "
+                                      "behind); its tokens are invalid -- rerun with B200_TP_ALLREDUCE=nccl to bypass")
         return self.h_tokens_np[kk][:n].tolist()
+
+    def drain(self) -> None:
+        """Forget steps that were launched but not collected (after a failed step)."""
+        torch.cuda.synchronize()
+        self._pending.clear()
 
     @torch.inference_mode()
     def capture_cudagraph(self):

@@ -20,6 +20,10 @@ from .. import _native as nat
 from .. import ops
 
 
+class PeerExchangeTimeout(RuntimeError):
+    pass
+
+
 class PeerReduce:
     def __init__(self, rows_cap: int, hidden: int, rank: int, world: int, device: torch.device):
         import torch.distributed._symmetric_memory as symm
@@ -95,8 +99,8 @@ class PeerReduce:
         """The kernel gives up (error flag, undefined output) rather than spin forever when a peer never announces
         its epoch; callers check after each batch of work so that such a run fails loudly instead of returning junk."""
         if int(self.state[2].item()) != 0:
-            raise RuntimeError("tensor-parallel peer exchange timed out (a rank stopped or fell >10 s behind); "
-                               "results of this call are invalid -- rerun with B200_TP_ALLREDUCE=nccl to bypass")
+            raise PeerExchangeTimeout("tensor-parallel peer exchange timed out (a rank stopped or fell >10 s behind); "
+                                      "results of this call are invalid -- rerun with B200_TP_ALLREDUCE=nccl to bypass")
 
     def next_out(self, rows: int) -> torch.Tensor:
         """Where the row-parallel GEMM of the next exchange must write its partial (the two buffers alternate)."""

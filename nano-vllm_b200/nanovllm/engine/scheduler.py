@@ -112,3 +112,16 @@ class Scheduler:
                 seq.status = SequenceStatus.FINISHED
                 bm.deallocate(seq)
                 self.running.remove(seq)
+
+    def abort_all(self) -> list[Sequence]:
+        """Retire every queued and running sequence, free its blocks and forget the prefix cache: the state after a
+        step whose results cannot be trusted.  Returns the aborted sequences."""
+        dropped = list(self.running) + list(self.waiting)
+        for seq in dropped:
+            if seq.block_table:
+                self.block_manager.deallocate(seq)
+            seq.status = SequenceStatus.FINISHED
+        self.running.clear()
+        self.waiting.clear()
+        self.block_manager.forget_prefix_cache()
+        return dropped

@@ -199,7 +199,7 @@ def embedding(ids: torch.Tensor, table: torch.Tensor, out: torch.Tensor | None =
     if out is None:
         out = torch.empty((n, hidden), dtype=table.dtype, device=table.device)
     lib = nat.load()
-    nat.check(lib.b200_embedding(ids.data_ptr(), table.data_ptr(), out.data_ptr(), n, hidden, _stream()))
+    nat.check(lib.b200_embedding(ids.data_ptr(), table.data_ptr(), out.data_ptr(), n, hidden, table.shape[0], _stream()))
     return out
 
 

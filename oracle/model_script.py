@@ -20,14 +20,18 @@ BLOCK = 16
 NUM_BLOCKS = 24
 
 
-def make_script(vocab: int, seed: int = 7) -> dict:
+def make_script(vocab: int, seed: int = 7, scale: int = 1, max_token: int | None = None) -> dict:
+    """``scale`` multiplies every length and the block size (scale 16 -> 256-token blocks, the only page size the
+    reference's flash-attn path accepts, config.py:22): the same seven steps at serving-size sequence lengths.
+    ``max_token`` bounds the token ids (default: the whole vocabulary)."""
     rnd = random.Random(seed)
-    tok = lambda n: [rnd.randint(0, vocab - 1) for _ in range(n)]
-    A, B, C = tok(37), tok(16), tok(70)
-    D = A[:32] + tok(9)           # shares A's first two full blocks
-    E, F = tok(20), tok(50)
+    hi = (max_token if max_token is not None else vocab) - 1
+    tok = lambda n: [rnd.randint(0, hi) for _ in range(n)]
+    A, B, C = tok(37 * scale), tok(16 * scale), tok(70 * scale)
+    D = A[:32 * scale] + tok(9 * scale)           # shares A's first two full blocks
+    E, F = tok(20 * scale), tok(50 * scale)
     forced = {name: tok(4) for name in "ABCDEF"}
-    return dict(block_size=BLOCK, num_blocks=NUM_BLOCKS, vocab=vocab,
+    return dict(block_size=BLOCK * scale, num_blocks=NUM_BLOCKS, vocab=vocab, scale=scale,
                 prompts=dict(A=A, B=B, C=C, D=D, E=E, F=F), forced=forced)
 
 
@@ -38,6 +42,8 @@ def _slots(table, start, end, bs=BLOCK):
 def script_steps(script: dict) -> list[dict]:
     """Plain-Python description of every step (lists of ints), independent of torch."""
     P, Fd = script["prompts"], script["forced"]
+    sc = script.get("scale", 1)
+    bs = script["block_size"]
     toks = {k: list(v) for k, v in P.items()}
     tables = dict(A=[0, 1, 2], B=[3], C=[4, 5, 6, 7, 8])
     steps = []
@@ -48,7 +54,7 @@ def script_steps(script: dict) -> list[dict]:
         for name, s, e in entries:
             ids += toks[name][s:e]
             pos += list(range(s, e))
-            slots += _slots(tables[name], s, e)
+            slots += _slots(tables[name], s, e, bs)
             cu_q.append(cu_q[-1] + e - s)
             cu_k.append(cu_k[-1] + e)
         bt = None
@@ -67,19 +73,19 @@ def script_steps(script: dict) -> list[dict]:
         w = max(len(tables[n]) for n in names)
         steps.append(dict(is_prefill=False, input_ids=[toks[n][-1] for n in names],
                           positions=[len(toks[n]) - 1 for n in names],
-                          slot_mapping=[_slots(tables[n], len(toks[n]) - 1, len(toks[n]))[0] for n in names],
+                          slot_mapping=[_slots(tables[n], len(toks[n]) - 1, len(toks[n]), bs)[0] for n in names],
                           context_lens=[len(toks[n]) for n in names],
                           block_tables=[tables[n] + [-1] * (w - len(tables[n])) for n in names]))
 
-    prefill([("A", 0, 37), ("B", 0, 16), ("C", 0, 70)], paged=False)          # 0: packed prefill
+    prefill([("A", 0, 37 * sc), ("B", 0, 16 * sc), ("C", 0, 70 * sc)], paged=False)   # 0: packed prefill
     decode(["A", "B", "C"], {"B": 9})                                          # 1: B crosses into a new block
     decode(["A", "B", "C"], {})                                                # 2
     tables["D"] = [0, 1, 10]
     tables["E"] = [11, 12]
-    prefill([("D", 32, 41), ("E", 0, 20)], paged=True)                         # 3: prefix hit + fresh prompt
+    prefill([("D", 32 * sc, 41 * sc), ("E", 0, 20 * sc)], paged=True)          # 3: prefix hit + fresh prompt
     tables["F"] = [13, 14, 15, 16]
-    prefill([("F", 0, 24)], paged=False)                                       # 4: first chunk
-    prefill([("F", 24, 50)], paged=True)                                       # 5: second chunk over the cache
+    prefill([("F", 0, 24 * sc)], paged=False)                                  # 4: first chunk
+    prefill([("F", 24 * sc, 50 * sc)], paged=True)                             # 5: second chunk over the cache
     decode(["A", "D", "F"], {})                                                # 6: mixed lengths 40 / 42 / 51
     return steps
 

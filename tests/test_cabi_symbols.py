@@ -37,12 +37,12 @@ def test_pdl_flavour_exports_the_same_abi():
     lib = ctypes.CDLL(str(pdl))
     for n in declared_symbols():
         assert hasattr(lib, n), f"{n} missing from the PDL flavour"
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
 
 
 def test_host_only_entry_points():
     lib = nat.load()
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == 2
     assert lib.b200_strerror(0) == b"ok"
     assert b"not bound" in lib.b200_strerror(-4)
     assert lib.b200_sm_count(None) == 0
@@ -144,7 +144,7 @@ def test_argument_validation_needs_no_gpu():
     assert lib.b200_silu_mul(p, p, 1, 12, None) == EINVAL               # inter must be a multiple of 8
     assert lib.b200_silu_mul(p + 2, p, 1, 8, None) == EINVAL            # misaligned
     assert lib.b200_silu_mul(p, p, 0, 8, None) == 0                     # empty batch: nothing to do
-    assert lib.b200_embedding(None, p, p, 1, 8, None) == EINVAL
+    assert lib.b200_embedding(None, p, p, 1, 8, 16, None) == EINVAL
     assert lib.b200_gather_tokens(p, None, p, 1, None) == EINVAL
     assert lib.b200_gather_tokens(p, p, p, 0, None) == 0
     assert lib.b200_kv_bind(None, p, p, 1, 1, 16, 1, 128) == EINVAL

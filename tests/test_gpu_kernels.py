@@ -117,6 +117,80 @@ def test_paged_decode_vs_oracle(ops, hq, hkv, bs, lens):
     assert torch.equal(got, again)
 
 
+def _poison_invalid_rows(ks, vs, tables, lens, bs, nblk):
+    """NaN in every cache row that no sequence owns (stale rows after the last token, unused pages)."""
+    valid = torch.zeros(nblk, bs, dtype=torch.bool)
+    for i, c in enumerate(lens):
+        for p in range(c):
+            valid[int(tables[i, p // bs]), p % bs] = True
+    nan = torch.tensor(float("nan"), dtype=torch.bfloat16)
+    for t in (ks, vs):
+        t[~valid] = nan
+    return valid
+
+
+@pytest.mark.parametrize("hq,hkv,bs,lens", [(8, 2, 64, [70, 5, 130, 17, 64]), (8, 1, 16, [33, 1, 47]), (32, 8, 256, [300, 1, 255, 513]),
+                                            (2, 2, 32, [31, 65])])
+def test_paged_decode_wide_groups_ignore_stale_rows(ops, hq, hkv, bs, lens):
+    """The tensor-core decode kernel (G >= 4, decode_mma.cu) always fetches whole 16-row TMA boxes: rows past the
+    context hold stale bytes.  Poison them with NaN -- P = 0 there, but 0 * NaN would poison the accumulator -- and
+    require the clean result.  (G = 1 rides along for the FMA kernel.)"""
+    nblk = sum((c + bs - 1) // bs for c in lens) + 2
+    kv, ks, vs = bind_random_cache(ops, 1, nblk, hkv, bs, seed=23)
+    tables = make_tables(lens, bs, nblk, seed=5)
+    ctx = torch.tensor(lens, dtype=torch.int32)
+    q = bf(len(lens), hq, 128, seed=3)
+    want = paged_decode_ref(q, ks[0], vs[0], ctx, tables, 0.1)
+    _poison_invalid_rows(ks[0], vs[0], tables, lens, bs, nblk)
+    kvp = torch.stack([to_physical(ks[0]).unsqueeze(0), to_physical(vs[0]).unsqueeze(0)]).cuda()
+    ops.bind_kv_cache(kvp)
+    got = ops.paged_decode(0, q.cuda(), tables.cuda(), ctx.cuda(), 0.1)
+    assert_close_bf16(got, want, f"decode G={hq // hkv} with NaN-poisoned stale rows")
+
+
+@pytest.mark.parametrize("bs", [16, 64, 256])
+def test_prefill_paged_ignores_stale_rows(ops, bs):
+    """Paged prefill (prefill_tc.cu) stages whole 64-key tiles; keys >= len_k of the last tile are stale page rows (or
+    page 0 when the tile runs past the block table).  NaN there must not reach the tcgen05 accumulator."""
+    hq, hkv = 8, 2
+    len_k = [300, 77, 130, 40, 65]
+    len_q = [44, 77, 1, 13, 65]
+    nblk = sum((c + bs - 1) // bs for c in len_k) + 2
+    kv, ks, vs = bind_random_cache(ops, 1, nblk, hkv, bs, seed=43)
+    tables = make_tables(len_k, bs, nblk, seed=8)
+    q = bf(sum(len_q), hq, 128, seed=7)
+    cu_q = torch.tensor([0] + list(torch.tensor(len_q).cumsum(0)), dtype=torch.int32)
+    cu_k = torch.tensor([0] + list(torch.tensor(len_k).cumsum(0)), dtype=torch.int32)
+    scale = 128 ** -0.5
+    want = varlen_prefill_ref(q, None, None, cu_q, cu_k, scale, tables, ks[0], vs[0], p_dtype=torch.bfloat16)
+    _poison_invalid_rows(ks[0], vs[0], tables, len_k, bs, nblk)
+    kvp = torch.stack([to_physical(ks[0]).unsqueeze(0), to_physical(vs[0]).unsqueeze(0)]).cuda()
+    ops.bind_kv_cache(kvp)
+    got = ops.paged_prefill(0, q.cuda(), None, None, cu_q.cuda(), cu_k.cuda(), max(len_q), max(len_k), scale,
+                            block_tables=tables.cuda(), num_kv_heads=hkv)
+    assert_close_bf16(got, want, f"paged prefill bs={bs} with NaN-poisoned stale rows")
+
+
+def test_prefill_packed_ignores_neighbouring_rows(ops):
+    """Packed prefill: the last 64-key tile of a sequence overlaps the NEXT sequence's rows (or runs past the end of
+    the batch).  Inf/NaN there must not leak into this sequence."""
+    hq, hkv = 4, 2
+    lens = [70, 3, 129]
+    tot = sum(lens)
+    q, k, v = bf(tot, hq, 128, seed=11), bf(tot, hkv, 128, seed=12), bf(tot, hkv, 128, seed=13)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    scale = 128 ** -0.5
+    # sequence 1 (rows 70..72) is all NaN/Inf: sequences 0 and 2 must be unaffected
+    k2, v2 = k.clone(), v.clone()
+    k2[70:73] = float("nan")
+    v2[70:73] = float("inf")
+    want = varlen_prefill_ref(q, k, v, cu, cu, scale, p_dtype=torch.bfloat16)
+    got = ops.paged_prefill(0, q.cuda(), k2.cuda(), v2.cuda(), cu.cuda(), cu.cuda(), max(lens), max(lens), scale).cpu()
+    keep = torch.ones(tot, dtype=torch.bool)
+    keep[70:73] = False
+    assert_close_bf16(got[keep], want[keep], "packed prefill next to a NaN/Inf sequence")
+
+
 def test_paged_decode_ignores_rows_beyond_context(ops):
     """Stale rows after the last valid token (and unused pages) may hold anything, even NaN."""
     hq, hkv, bs, lens = 4, 2, 64, [70, 5, 130]

@@ -18,8 +18,14 @@ def main():
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    backend = os.environ.get("B200_TP_BACKEND", "nccl")
+    if os.environ.get("B200_TP_ONE_DEVICE") == "1":          # every rank on GPU 0 (single-GPU boxes; gloo collectives)
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
     from nanovllm import LLM, SamplingParams
     from nanovllm.utils.synthetic import PRESETS, make_model_dir, random_weights
     preset = os.environ.get("TP_PRESET", "tiny-g4")
@@ -49,7 +55,8 @@ def main():
             if sp.temperature == 0.0:
                 a, b, _ = check_greedy_against_oracle(oracle, p, t)
                 n, d = n + a, d + b
-        result.update(greedy_tokens=n, differ_from_oracle_argmax=d, ok=True)
+        result.update(greedy_tokens=n, differ_from_oracle_argmax=d, ok=True, backend=backend,
+                      peer_exchange=llm.model_runner.model.peer is not None)
         print("TP_RESULT " + json.dumps(result), flush=True)
     llm.exit()
     dist.barrier()
