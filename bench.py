@@ -234,7 +234,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # roofline leg: the decode kernel alone, on the run's own decode-step shapes
 # ------------------------------------------------------------------------------------------------
-def decode_roofline(llm, sample_every: int = 24):
+def decode_roofline(llm, sample_every: int = 24, requests=None):
     """Replays the paged-decode launches (all layers) of every `sample_every`-th decode step of the benchmark
     schedule, timed with CUDA events on the launching stream, L2 flushed before each sampled step.
     Algorithmic bytes per launch = sum(ctx) * 2 * Hkv * D * 2 B (K and V read once) + q/out + metadata."""
@@ -250,7 +250,7 @@ def decode_roofline(llm, sample_every: int = 24):
     m = runner.model
     L = len(m.layers)
     cfg = llm.config
-    prompts, max_tokens = bench_requests(0)
+    prompts, max_tokens = requests if requests is not None else bench_requests(0)
     Sequence.counter = itertools.count()
     sched = Scheduler(SimpleNamespace(max_num_seqs=cfg.max_num_seqs, max_num_batched_tokens=cfg.max_num_batched_tokens,
                                       eos=-1, kvcache_block_size=cfg.kvcache_block_size,
@@ -293,7 +293,7 @@ def decode_roofline(llm, sample_every: int = 24):
     peaks = load_peaks()
     achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
     first = per_step[0]
-    first_gbs = (first[2] * 4096 * (m.num_kv_heads / 8)) / (first[3] * 1e-6) / 1e9
+    first_gbs = (first[2] * 2 * m.num_kv_heads * m.head_dim * 2) / (first[3] * 1e-6) / 1e9
     traffic, traffic_is = ncu_traffic()
     # decode GB/s by batch-size bucket (the second half of the run lives at small batches)
     buckets = {}
@@ -305,9 +305,11 @@ def decode_roofline(llm, sample_every: int = 24):
         bb[2] += 1
     by_batch = [{"batch_le": k, "steps_sampled": v[2], "avg_launch_us": v[1] / v[2], "GB/s": v[0] / (v[1] * 1e-6) / 1e9,
                  "frac": v[0] / (v[1] * 1e-6) / 1e9 / peaks["hbm_gbs"]} for k, v in sorted(buckets.items())]
-    return {"bound": "hbm", "kernel": "paged_decode_kernel<G=2>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    G = m.num_heads // m.num_kv_heads
+    return {"bound": "hbm", "kernel": f"paged_decode_kernel<G={G}>" if G <= 2 else f"paged_decode_mma_kernel<G={G}>", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "peak_source": peaks["source"], "frac_of_8TBs_spec": achieved / 8000.0,
-            "traffic": traffic, "traffic_is": traffic_is + " (vs 587.2 MB algorithmic for that launch)",
+            "traffic": traffic if requests is None else None,
+            "traffic_is": (traffic_is + " (vs 587.2 MB algorithmic for that launch)") if requests is None else "not captured for this workload",
             "launches_timed": launches, "avg_launch_us": tot_ms * 1000.0 / launches,
             "bytes_per_launch_avg": tot_bytes / launches,
             "batch256_step0": {"batch": first[1], "sum_ctx": first[2], "launch_us": first[3], "GB/s": first_gbs,

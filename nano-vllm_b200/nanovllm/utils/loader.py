@@ -29,14 +29,30 @@ def load_model(model, path: str, allow_random: bool = False, seed: int = 0) -> i
     return n
 
 
-def _random_fill(model, seed: int) -> int:
-    from .synthetic import random_weights
+def _random_fill(model, seed: int, init_std: float = 0.02) -> int:
+    """Seeded random weights for a directory that has none (benchmarks at 8B / 32B dimensions: no checkpoint exists
+    offline).  On a CUDA model every tensor is drawn ON THE DEVICE from a generator keyed by (seed, parameter name) at
+    its FULL shape and handed to ``load_hf_tensor``, which slices this rank's shard -- so all tensor-parallel ranks hold
+    shards of one well-defined model without 64 GB of host memory or a broadcast.  On a CPU model the values are
+    ``synthetic.random_weights`` (what the tests compare against)."""
+    from .synthetic import random_weights, weight_shapes
     c = model.cfg
     dims = dict(hidden_size=c.hidden_size, num_hidden_layers=c.num_hidden_layers,
                 num_attention_heads=c.num_attention_heads, num_key_value_heads=c.num_key_value_heads,
                 head_dim=model.head_dim, intermediate_size=c.intermediate_size, vocab_size=c.vocab_size,
                 tie_word_embeddings=model.tie)
-    ws = random_weights(dims, seed)
-    for name, w in ws.items():
-        model.load_hf_tensor(name, w)
-    return len(ws)
+    if model.device.type != "cuda":
+        ws = random_weights(dims, seed)
+        for name, w in ws.items():
+            model.load_hf_tensor(name, w)
+        return len(ws)
+    import zlib
+    gen = torch.Generator(device=model.device)
+    shapes = weight_shapes(dims)
+    for name, shape in shapes.items():
+        gen.manual_seed((seed << 32) ^ zlib.crc32(name.encode()))
+        w = torch.randn(shape, generator=gen, device=model.device, dtype=torch.float32)
+        w = (1.0 + 0.1 * w) if len(shape) == 1 else init_std * w
+        model.load_hf_tensor(name, w.to(torch.bfloat16))
+        del w
+    return len(shapes)

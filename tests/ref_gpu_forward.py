@@ -3,7 +3,10 @@ its Triton store_kvcache, its loader) on cuda:0 over a teacher-forced serving sc
 TEST INFRASTRUCTURE ONLY -- executed as a subprocess by tests/test_gpu_reference_forward.py because the reference
 and the product both own the package name ``nanovllm``.
 
-    python tests/ref_gpu_forward.py <model_dir> <script.json> <out.npz>
+    python tests/ref_gpu_forward.py <model_dir> <script.json> <out.npz> [--dropin]
+
+With --dropin the same reference runs with INTEGRATION.md's option B applied (integration/b200_binding.py): only
+Attention.forward and the cache allocation line change, every other module is the reference's own.
 
 What it does is what the reference's ModelRunner does in eager mode (engine/model_runner.py:17-48,103-121,195-220):
 process group of one, bf16 default dtype on cuda, load_model, one [2, L, nblk, bs, Hkv, D] cache bound to every
@@ -19,6 +22,7 @@ REF = os.path.join(ROOT, "baseline", "_ref")
 
 def main():
     model_dir, script_path, out_path = sys.argv[1:4]
+    dropin = "--dropin" in sys.argv[4:]
     sys.path.insert(0, REF)
     sys.path.insert(1, ROOT)
     import numpy as np
@@ -42,14 +46,21 @@ def main():
     model = Qwen3ForCausalLM(hf)
     load_model(model, model_dir)
     head_dim = getattr(hf, "head_dim", hf.hidden_size // hf.num_attention_heads)
-    kv = torch.zeros(2, hf.num_hidden_layers, script["num_blocks"], script["block_size"], hf.num_key_value_heads, head_dim)
-    layer = 0
-    for module in model.modules():                       # model_runner.py:116-121
-        if hasattr(module, "k_cache") and hasattr(module, "v_cache"):
-            module.k_cache = kv[0, layer]
-            module.v_cache = kv[1, layer]
-            layer += 1
-    assert layer == hf.num_hidden_layers
+    if dropin:
+        from integration import b200_binding as b200
+        b200.init(0)
+        b200.patch()
+        kv = b200.allocate_kv_cache(model, hf.num_hidden_layers, script["num_blocks"], script["block_size"],
+                                    hf.num_key_value_heads, head_dim, hf.num_attention_heads)
+    else:
+        kv = torch.zeros(2, hf.num_hidden_layers, script["num_blocks"], script["block_size"], hf.num_key_value_heads, head_dim)
+        layer = 0
+        for module in model.modules():                       # model_runner.py:116-121
+            if hasattr(module, "k_cache") and hasattr(module, "v_cache"):
+                module.k_cache = kv[0, layer]
+                module.v_cache = kv[1, layer]
+                layer += 1
+        assert layer == hf.num_hidden_layers
     torch.set_default_device("cpu")
 
     @torch.inference_mode()

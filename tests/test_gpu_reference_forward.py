@@ -40,9 +40,9 @@ def _dims(layers: int) -> dict:
     return d
 
 
-def _run_reference(model_dir: str, script: dict, tmp: str, compiled: bool):
+def _run_reference(model_dir: str, script: dict, tmp: str, compiled: bool, dropin: bool = False):
     import numpy as np
-    sp, op = os.path.join(tmp, "script.json"), os.path.join(tmp, f"ref_{int(compiled)}.npz")
+    sp, op = os.path.join(tmp, "script.json"), os.path.join(tmp, f"ref_{int(compiled)}_{int(dropin)}.npz")
     with open(sp, "w") as f:
         json.dump(script, f)
     env = dict(os.environ)
@@ -50,7 +50,7 @@ def _run_reference(model_dir: str, script: dict, tmp: str, compiled: bool):
     if not compiled:
         env["TORCH_COMPILE_DISABLE"] = "1"
     env["REF_FORWARD_PORT"] = str(29731 + (os.getpid() % 200))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_gpu_forward.py"), model_dir, sp, op],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_gpu_forward.py"), model_dir, sp, op] + (["--dropin"] if dropin else []),
                        env=env, capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
         return None, (r.stdout + r.stderr)[-2000:]
@@ -140,3 +140,36 @@ def test_product_vs_reference_gpu_forward_vs_fp32_truth(layers, tmp_path):
                                          worst_ref_vs_truth=worst_r, worst_ours_vs_ref=max(s["ours_vs_ref"] for s in steps),
                                          greedy_rows=rows, all_three_agree=agree_all, ours_eq_ref=ours_eq_ref,
                                          rows_with_clear_fp32_winner=decided, of_which_all_agree=decided_ok, steps=steps))
+
+
+def test_reference_tree_with_only_the_operator_swapped(tmp_path):
+    """INTEGRATION.md option B, executed: the reference's own model (its linears, norms, RoPE, LM head; eager) with ONLY
+    Attention.forward and the cache layout line changed to libb200attn.so (integration/b200_binding.py), against the
+    unmodified reference (flash-attn + Triton store) on the same weights and the same serving script."""
+    if not os.path.isdir(REF):
+        pytest.skip("baseline/_ref (the installed reference) is not present")
+    from nanovllm.utils.synthetic import make_model_dir
+    dims = _dims(4)
+    model_dir = make_model_dir(str(tmp_path / "model"), dims, seed=99, tokenizer=False)
+    script = make_script(dims["vocab_size"], scale=16)
+    ref, err = _run_reference(model_dir, script, str(tmp_path), compiled=False)
+    assert ref is not None, err
+    got, err = _run_reference(model_dir, script, str(tmp_path), compiled=False, dropin=True)
+    assert got is not None, err
+    rows = same = 0
+    worst = 0.0
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert g.shape == r.shape and torch.isfinite(g).all()
+        rel = ((g - r).norm() / r.norm()).item()
+        worst = max(worst, rel)
+        assert rel < 1e-2, f"step {i}: logits of the reference with our operator vs the unmodified reference: relative L2 {rel}"
+        ulp = 2 ** -8 * r.abs().max().item()
+        top2 = r.topk(2, dim=-1).values
+        for row in range(g.shape[0]):
+            rows += 1
+            eq = int(g[row].argmax()) == int(r[row].argmax())
+            same += eq
+            if (top2[row, 0] - top2[row, 1]).item() > 8 * ulp:
+                assert eq, f"step {i} row {row}: greedy token differs from the unmodified reference"
+    record("integration_option_b", dict(layers=4, dims="qwen3-0.6b", worst_rel_l2_vs_unmodified_reference=worst,
+                                        greedy_rows=rows, greedy_equal=same))
