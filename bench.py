@@ -260,6 +260,10 @@ def decode_roofline(llm, sample_every: int = 24, requests=None):
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     q = torch.randn(runner.cap_bs, m.num_heads, m.head_dim, device="cuda").to(torch.bfloat16)
     out = torch.empty_like(q)
+    t_w = time.perf_counter()                       # the GPU idled during the host-side legs: bring the clocks back up
+    while time.perf_counter() - t_w < 0.5:
+        flush.fill_(0)
+        torch.cuda.synchronize()
     tot_bytes = tot_ms = 0.0
     launches = 0
     dstep = 0

@@ -2,6 +2,8 @@
 // They replace the reference's Triton KV scatter and its five @torch.compile sites (SURVEY.md 2b,
 // K1 and K5-K8): fp32 math, one rounding at every stored output (what Inductor generates on a
 // GPU), 128-bit coalesced global accesses, warp-shuffle reductions.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -120,7 +122,8 @@ __global__ void __launch_bounds__(128) rmsnorm_warp_kernel(const __nv_bfloat16* 
 template <bool HAS_RES>
 bool launch_rmsnorm_warp(const __nv_bfloat16* x, int64_t xs, __nv_bfloat16* res, const __nv_bfloat16* w, __nv_bfloat16* out,
                          int64_t os, int rows, int cols, float eps, cudaStream_t st) {
-    if (cols % 256 || cols > 2048 || rows > 4096) return false;       // big prefill batches keep the block-per-row kernel
+    static const int max_rows = [] { const char* e = getenv("B200_NORM_WARP_MAX_ROWS"); return e ? atoi(e) : 4096; }();
+    if (cols % 256 || cols > 2048 || rows > max_rows) return false;   // beyond that the block-per-row kernel (tuning knob)
     const unsigned grid = (rows + 3) / 4;
     switch (cols / 256) {
         case 1: B200_LAUNCH((rmsnorm_warp_kernel<HAS_RES, 1>), grid, 128, 0, st, x, xs, res, w, out, os, rows, eps); return true;
@@ -196,6 +199,77 @@ __global__ void __launch_bounds__(128) qknorm_rope_store_kernel(
     if (!is_q && slot >= 0) {
         const int kvh = head - hq;
         *reinterpret_cast<uint4*>(k_cache + (crow + ((int64_t)kvh << block_shift)) * B200_HEAD_DIM + j * 8) = outv;
+    }
+}
+
+// The same op for prefill-size batches: one HALF-warp per TOKEN walking over its heads.  Lane j owns the same 8 dims of
+// every head, so positions / cos / sin / norm weights / the cache row are fetched once per token instead of once per
+// (token, head), there is no 64-bit division, and U independent 16-byte loads per lane are in flight.
+template <int U>
+__global__ void __launch_bounds__(128) qknorm_rope_store_tok_kernel(
+    __nv_bfloat16* qkv, int64_t stride, int hq, int hkv, const int64_t* __restrict__ positions,
+    const __nv_bfloat16* __restrict__ qw, const __nv_bfloat16* __restrict__ kw,
+    const float* __restrict__ cos_sin, float eps, const int32_t* __restrict__ slot_mapping,
+    __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, int block_shift, int n) {
+    B200_PDL_SYNC();
+    const int heads = hq + 2 * hkv;
+    const int t_raw = blockIdx.x * 8 + (threadIdx.x >> 4);
+    const bool live = t_raw < n;                       // a dead half-warp still takes part in the full-warp shuffles
+    const int tok = live ? t_raw : n - 1;
+    const int j = threadIdx.x & 15;
+    __nv_bfloat16* row = qkv + (int64_t)tok * stride + j * 8;
+
+    int slot = -1;
+    if (slot_mapping != nullptr && k_cache != nullptr) slot = slot_mapping[tok];
+    const int64_t crow = slot < 0 ? 0
+        : ((((int64_t)(slot >> block_shift)) * hkv) << block_shift) + (slot & ((1 << block_shift) - 1));
+    float qwf[8], kwf[8];
+    unpack8(*reinterpret_cast<const uint4*>(qw + j * 8), qwf);
+    unpack8(*reinterpret_cast<const uint4*>(kw + j * 8), kwf);
+    const float* cs = cos_sin + positions[tok] * B200_HEAD_DIM + (j & 7) * 8;
+    const float4 c0 = *reinterpret_cast<const float4*>(cs), c1 = *reinterpret_cast<const float4*>(cs + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(cs + 64), s1 = *reinterpret_cast<const float4*>(cs + 68);
+    const float cosv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sinv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+
+    for (int h0 = 0; h0 < heads; h0 += U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (h0 + u < heads) raw[u] = *reinterpret_cast<const uint4*>(row + (h0 + u) * B200_HEAD_DIM);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int head = h0 + u;
+            if (head >= heads) break;                  // uniform across the warp
+            if (head >= hq + hkv) {                    // a value head: scatter only
+                if (live && slot >= 0)
+                    *reinterpret_cast<uint4*>(v_cache + (crow + ((int64_t)(head - hq - hkv) << block_shift)) * B200_HEAD_DIM + j * 8) = raw[u];
+                continue;
+            }
+            const bool is_q = head < hq;
+            float x[8];
+            unpack8(raw[u], x);
+            float ss = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(x[e], x[e], ss);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float rstd = 1.0f / sqrtf(ss / (float)B200_HEAD_DIM + eps);
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float nv = round_bf16(__fmul_rn(__fmul_rn(x[e], rstd), is_q ? qwf[e] : kwf[e]));
+                const float other = __shfl_xor_sync(0xffffffffu, nv, 8);
+                y[e] = (j < 8) ? __fsub_rn(__fmul_rn(nv, cosv[e]), __fmul_rn(other, sinv[e]))
+                               : __fadd_rn(__fmul_rn(nv, cosv[e]), __fmul_rn(other, sinv[e]));
+            }
+            if (live) {
+                const uint4 outv = pack8(y);
+                *reinterpret_cast<uint4*>(row + head * B200_HEAD_DIM) = outv;
+                if (!is_q && slot >= 0)
+                    *reinterpret_cast<uint4*>(k_cache + (crow + ((int64_t)(head - hq) << block_shift)) * B200_HEAD_DIM + j * 8) = outv;
+            }
+        }
     }
 }
 
@@ -312,6 +386,14 @@ extern "C" int b200_qknorm_rope_store(b200_ctx* ctx, int layer, void* qkv, int64
         kc = ctx->k_layer(layer);
         vc = ctx->v_layer(layer);
         shift = ctx->block_shift;
+    }
+    static const int tok_min = [] { const char* e = getenv("B200_QKNORM_TOK_MIN"); return e ? atoi(e) : 2048; }();
+    if (n >= tok_min) {             // prefill-size batch: one half-warp per token (see the kernel)
+        B200_LAUNCH((qknorm_rope_store_tok_kernel<8>), (unsigned)((n + 7) / 8), 128, 0, static_cast<cudaStream_t>(stream),
+            static_cast<__nv_bfloat16*>(qkv), qkv_stride0, num_q_heads, num_kv_heads, positions,
+            static_cast<const __nv_bfloat16*>(q_norm_weight), static_cast<const __nv_bfloat16*>(k_norm_weight),
+            cos_sin, eps, slot_mapping, kc, vc, shift, n);
+        return b200_launch_status(ctx);
     }
     const int64_t units = (int64_t)n * (num_q_heads + 2 * num_kv_heads);       // one half-warp each, 8 per block
     const unsigned blocks = (unsigned)((units + 7) / 8);

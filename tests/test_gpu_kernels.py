@@ -381,14 +381,16 @@ def test_add_rmsnorm(ops, rows, cols):
     assert_close_bf16(got_y, want_y, "add_rmsnorm", ulps=1.01)
 
 
-@pytest.mark.parametrize("hq,hkv,bs,cached", [(4, 2, 16, True), (16, 8, 256, True), (8, 1, 64, False)])
-def test_qknorm_rope_store(ops, hq, hkv, bs, cached):
-    n, nblk, theta = 29, 5, 1e6
+@pytest.mark.parametrize("n", [29, 2501])          # 2501: the token-major kernel used for prefill-size batches
+@pytest.mark.parametrize("hq,hkv,bs,cached", [(4, 2, 16, True), (16, 8, 256, True), (8, 1, 64, False), (2, 1, 32, True)])
+def test_qknorm_rope_store(ops, hq, hkv, bs, cached, n):
+    nblk, theta = max(5, (n + bs - 1) // bs + 2), 1e6
     kv, ks, vs = bind_random_cache(ops, 2, nblk, hkv, bs, seed=51)
     qkv = bf(n, (hq + 2 * hkv) * 128, seed=8)
     qw, kw = (1 + 0.1 * torch.randn(128)).to(torch.bfloat16), (1 + 0.1 * torch.randn(128)).to(torch.bfloat16)
     table = rope_table(128, 4096, theta)
-    pos = torch.tensor(random.Random(3).sample(range(4096), n), dtype=torch.int64)
+    rp = random.Random(3)
+    pos = torch.tensor([rp.randrange(4096) for _ in range(n)], dtype=torch.int64)
     slots = torch.tensor(random.Random(4).sample(range(nblk * bs), n), dtype=torch.int32)
     slots[3] = -1
     q = qkv[:, :hq * 128].view(n, hq, 128)
