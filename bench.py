@@ -264,7 +264,7 @@ def decode_roofline(llm, sample_every: int = 24, requests=None):
     while time.perf_counter() - t_w < 0.5:
         flush.fill_(0)
         torch.cuda.synchronize()
-    tot_bytes = tot_ms = 0.0
+    tot_bytes = tot_ms = tot_unique = 0.0
     launches = 0
     dstep = 0
     per_step = []
@@ -286,6 +286,9 @@ def decode_roofline(llm, sample_every: int = 24, requests=None):
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1)
                 kv_bytes = int(a["context_lens"].sum()) * 2 * m.num_kv_heads * m.head_dim * 2
+                # pages shared between sequences (prefix cache) are fetched from HBM once and hit in L2 afterwards
+                uniq_pages = int(np.unique(a["block_tables"][a["block_tables"] >= 0]).size)
+                tot_unique += L * min(kv_bytes, uniq_pages * cfg.kvcache_block_size * 2 * m.num_kv_heads * m.head_dim * 2)
                 io_bytes = n * m.num_heads * m.head_dim * 2 * 2 + n * (bt.shape[1] + 1) * 4
                 tot_bytes += L * (kv_bytes + io_bytes)
                 tot_ms += ms
@@ -319,6 +322,10 @@ def decode_roofline(llm, sample_every: int = 24, requests=None):
             "batch256_step0": {"batch": first[1], "sum_ctx": first[2], "launch_us": first[3], "GB/s": first_gbs,
                                "frac_measured_peak": first_gbs / peaks["hbm_gbs"], "frac_8TBs": first_gbs / 8000.0},
             "by_batch": by_batch,
+            "unique_page_bytes_per_launch_avg": tot_unique / launches,
+            "unique_page_GB/s": tot_unique / (tot_ms * 1e-3) / 1e9,
+            "unique_page_note": "upper bound of the HBM bytes when sequences share pages (prefix cache): every distinct page "
+                                "counted once and in full; equals the algorithmic figure when no page is shared",
             "how": f"CUDA events around {L} back-to-back launches (one per layer, distinct KV) for every {sample_every}th "
                    "decode step of the benchmark schedule, L2 flushed (512 MiB write) before each sampled step"}
 
@@ -433,6 +440,7 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
 
     runner.begin_profile()
+    llm.loop_stats.update(steps=0, total_s=0.0, wait_s=0.0)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -447,6 +455,7 @@ def run_b200_arm(args):
     ev_ms = e0.elapsed_time(e1)
     log(f"timed region: {args.steps} passes in {wall:.2f}s")
     prof = runner.end_profile()
+    ls = dict(llm.loop_stats)
     t = torch.tensor([ev_ms, prof["device_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -500,7 +509,12 @@ def run_b200_arm(args):
                                            "e2e_vs_baseline",
                       "e2e_vs_baseline": e2e / README_TOK_S,
                       "kv_blocks": llm.config.num_kvcache_blocks, "init_s": round(init_s, 1),
-                      "sample_seed": runner.sample_seed},
+                      "sample_seed": runner.sample_seed,
+                      "host_loop": {"engine_steps": ls["steps"], "ms_per_step": 1e3 * ls["total_s"] / max(ls["steps"], 1),
+                                    "host_own_work_ms_per_step": 1e3 * (ls["total_s"] - ls["wait_s"]) / max(ls["steps"], 1),
+                                    "blocked_on_gpu_ms_per_step": 1e3 * ls["wait_s"] / max(ls["steps"], 1),
+                                    "what": "rank 0's step loop: wall time per engine step, the part spent waiting for the GPU's "
+                                            "tokens, and the rest (schedule + postprocess + metadata staging + launches)"}},
         }
         if parity is not None:
             line["parity"] = parity

@@ -81,6 +81,9 @@ class LLMEngine:
         config.eos = self.tokenizer.eos_token_id if self.tokenizer.eos_token_id is not None else -1
         self.scheduler = Scheduler(config)            # after the runner: it needs num_kvcache_blocks
         self._closed = False
+        # step-loop accounting (seconds): total wall time of the loop, and the part of it spent blocked on the GPU;
+        # total - wait is the host's own work (scheduling, metadata staging, launches, detokenisation)
+        self.loop_stats = {"steps": 0, "total_s": 0.0, "wait_s": 0.0}
         atexit.register(self.exit)
 
     # ---- rank-0 -> mirror ranks control channel (spawn mode only) --------------------------
@@ -211,6 +214,7 @@ class LLMEngine:
         PENDING = -1
         if sched.is_finished():
             return
+        st = self.__dict__.setdefault("loop_stats", {"steps": 0, "total_s": 0.0, "wait_s": 0.0})   # host time: waiting vs own work
         seqs, is_prefill = sched.schedule()
         runner.call("launch", seqs, is_prefill)
         t0 = perf_counter()
@@ -229,18 +233,24 @@ class LLMEngine:
                         src = [row_of.get(id(s), -1) for s in nxt[0]]
                         runner.launch(nxt[0], False, runner.stage_decode(nxt[0]), src)
                         launched = True
+                tw = perf_counter()
                 tokens = runner.call("collect")
+                st["wait_s"] += perf_counter() - tw
                 for s, b, t in zip(seqs, before, tokens):
                     if s.num_tokens != b:                       # a token was appended: give it its value
                         s.token_ids[-1] = t
                         s.last_token = t
             else:
+                tw = perf_counter()
                 tokens = runner.call("collect")
+                st["wait_s"] += perf_counter() - tw
                 sched.postprocess(seqs, tokens, is_prefill)
                 if not sched.is_finished():
                     nxt = sched.schedule()
             now = perf_counter()
             on_step([s for s in seqs if s.is_finished], num_tokens, max(now - t0, 1e-9))
+            st["steps"] += 1
+            st["total_s"] += now - t0
             t0 = now
             if nxt is None:
                 return

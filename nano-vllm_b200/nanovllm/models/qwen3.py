@@ -79,8 +79,10 @@ class Qwen3ForCausalLM:
         # Staged for the next round and OFF by default: B200_LINEAR=tc routes the decode-size projections through
         # csrc/linear_tc.cu (tcgen05, SiluAndMul / split-K add+RMSNorm fused) instead of cuBLAS.  That kernel has not
         # run on a GPU yet.  B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
-        self.tc_linear = os.environ.get("B200_LINEAR", "cublas") == "tc"
-        self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "32,32,64,8,64,8,0").split(",")]
+        mode = os.environ.get("B200_LINEAR", "cublas")
+        self.tc_linear = mode in ("tc", "rows")
+        self.tc_cols = mode == "tc"               # "rows": only the row-parallel o_proj / down_proj (split-K + fused add-norm)
+        self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,0").split(",")]
         self.tc_max_rows = 256
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
@@ -193,7 +195,7 @@ class Qwen3ForCausalLM:
                 residual, x = h, ops.rmsnorm(h, L.ln1, eps)
             else:
                 x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln1)
-            qkv = ops.linear(x, L.qkv, ops.EPI_BF16, cfg[0], pdl=bool(cfg[6])) if tc else F.linear(x, L.qkv)
+            qkv = ops.linear(x, L.qkv, ops.EPI_BF16, cfg[0], pdl=bool(cfg[6])) if (tc and self.tc_cols) else F.linear(x, L.qkv)
             cached = attn.k_cache.numel() > 0
             t = qkv.shape[0]
             if cached and not ctx.is_prefill and t <= self.fused_decode_max_batch:
@@ -209,7 +211,7 @@ class Qwen3ForCausalLM:
                 o = attn(q, k, v, kv_stored=True)
             h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o, (cfg[2], cfg[3]) if tc else None)
             x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln2)
-            if tc:
+            if tc and self.tc_cols:
                 act = ops.linear(x, L.gate_up, ops.EPI_SILU, cfg[1], pdl=bool(cfg[6]))
             else:
                 act = ops.silu_mul(F.linear(x, L.gate_up))

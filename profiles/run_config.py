@@ -16,7 +16,7 @@ throughput (wall clock around generate(), after a warm-up generate), the decode 
 shapes (CUDA events, rank 0's shard), KV sizing, and a parity leg: greedy requests whose tokens must agree (a) between
 all ranks, (b) between twin prompts served in different batches / through the prefix cache, and (c) -- configs 3 and 4 use
 the same model and the same greedy prompts -- between the 1-GPU run and the TP4 run (tokens of config 3 are saved to
-profiles/r02_config3_greedy_tokens.json and compared by config 4 when the file is present).
+gpurun_out/r02_config3_greedy_tokens.json, committed as profiles/r02_config3_greedy_tokens.json and compared by config 4).
 """
 import json
 import os
@@ -27,7 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "nano-vllm_b200")]
 os.environ.setdefault("NANOVLLM_ALLOW_RANDOM_INIT", "1")
-GREEDY_FILE = os.path.join(ROOT, "profiles", "r02_config3_greedy_tokens.json")
+GREEDY_FILE = os.path.join(ROOT, "profiles", "r02_config3_greedy_tokens.json")          # committed copy, read by config 4
+GREEDY_OUT = os.path.join(ROOT, "gpurun_out", "r02_config3_greedy_tokens.json")          # written by config 3 (gpurun merges gpurun_out/ back)
 
 
 def requests_for(cfg: int):
@@ -133,7 +134,8 @@ def main():
         peer = getattr(m, "peer", None)
         parity["tp_exchange"] = "nccl" if peer is None else ("nvls" if peer.nvls else "peer-memory kernel")
     if rank == 0 and cfg == 3:
-        with open(GREEDY_FILE, "w") as f:
+        os.makedirs(os.path.dirname(GREEDY_OUT), exist_ok=True)
+        with open(GREEDY_OUT, "w") as f:
             json.dump({"what": "greedy tokens of profiles/run_config.py greedy_requests() on Qwen3-8B dims, 1 GPU", "tokens": toks}, f)
     if rank == 0 and cfg == 4 and os.path.exists(GREEDY_FILE):
         ref = json.load(open(GREEDY_FILE))["tokens"]

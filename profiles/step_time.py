@@ -48,7 +48,7 @@ def main():
         seqs = list(llm.scheduler.running)
         a = runner.decode_arrays(seqs)
         import numpy as np
-        ctx = torch.from_numpy(a["context_lens"]).cuda()
+        ctx = torch.from_numpy(a["context_lens"] - 1).cuda()      # tokens whose K/V are stored (the newest has no page yet)
         bt = torch.from_numpy(np.ascontiguousarray(a["block_tables"])).cuda()
         q = torch.randn(len(seqs), m.num_heads, m.head_dim, device="cuda").to(torch.bfloat16)
         o = torch.empty_like(q)
