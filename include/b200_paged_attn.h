@@ -241,6 +241,28 @@ int b200_lm_head_sample(const void* hidden, int64_t hidden_stride0, const void* 
 int b200_add_rmsnorm_partials(const float* partials, int splits, void* residual, const void* weight, void* out,
                               int rows, int cols, float eps, int flags, void* stream);
 
+/* The tail of a decoder layer for a decode-size batch on one GPU, as ONE persistent kernel (csrc/layer_tail.cu):
+ *   o_proj -> residual add + RMSNorm -> gate_up_proj + SiluAndMul -> down_proj -> residual add + RMSNorm [-> next qkv_proj]
+ * i.e. RowParallelLinear o_proj + RMSNorm.add_rms_forward + Qwen3MLP + the next layer's input_layernorm and
+ * QKVParallelLinear (reference models/qwen3.py:72-76,87,91-117,146-159; layers/linear.py; layers/layernorm.py:28-40;
+ * layers/activation.py:8-11).  Rounding points are the reference's: every projection is rounded to bf16 where F.linear's
+ * output is bf16, the norms use the un-rounded fp32 sum.
+ *   attn_out [rows, q_size] bf16 (row stride attn_stride0); residual [rows, hidden] bf16, updated in place (twice);
+ *   w_o [hidden, q_size], w_gate_up [2*inter, hidden] (gate rows, then up rows), w_down [hidden, inter], bf16 contiguous;
+ *   ln_mid / ln_next: the two RMSNorm weights; x_next [rows, hidden] bf16: the normalised input of the next layer;
+ *   w_qkv_next [qkv_n, hidden] + qkv_out [rows, qkv_n] (row stride qkv_stride0): optional (NULL: stop after x_next);
+ *   splits_o / splits_down: split-K factors of the two hidden-wide projections (partials are summed in split order);
+ *   workspace: b200_layer_tail_workspace_bytes(rows, hidden, inter, max(splits)) bytes, 256-byte aligned, ZERO before
+ *   the first use (it holds the grid-barrier state); rows <= 1024; hidden, q_size, inter multiples of 64.
+ * Launched cooperatively (one CTA per SM, all resident); graph-capturable; a barrier that cannot complete sets the error
+ * word at workspace + 8 instead of hanging. */
+size_t b200_layer_tail_workspace_bytes(int max_rows, int hidden, int inter, int max_splits);
+int b200_layer_tail(b200_ctx* ctx, const void* attn_out, int64_t attn_stride0, void* residual, const void* w_o,
+                    const void* ln_mid, const void* w_gate_up, const void* w_down, const void* ln_next, void* x_next,
+                    const void* w_qkv_next, void* qkv_out, int64_t qkv_stride0, int qkv_n, void* workspace,
+                    size_t workspace_bytes, int rows, int hidden, int q_size, int inter, float eps, int splits_o,
+                    int splits_down, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

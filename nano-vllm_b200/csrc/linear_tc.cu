@@ -365,6 +365,15 @@ bool cached_map(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows
     return true;
 }
 
+}  // namespace
+
+// shared with layer_tail.cu
+bool b200_cached_tensor_map(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t stride, uint32_t box_rows) {
+    return cached_map(out, base, cols, rows, stride, box_rows);
+}
+
+namespace {
+
 template <int BN, int EPI, bool DEEP, int CL>
 int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
     using C = Cfg<BN, DEEP>;

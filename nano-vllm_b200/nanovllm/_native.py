@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_linear": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_add_rmsnorm_partials": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_lm_head_sample": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "b200_layer_tail_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200_layer_tail": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _sz, _i, _i, _i, _i, _f, _i, _i, _vp]),
 }
 
 _lib = None

@@ -84,6 +84,15 @@ class Qwen3ForCausalLM:
         self.tc_cols = mode == "tc"               # "rows": only the row-parallel o_proj / down_proj (split-K + fused add-norm)
         self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,0").split(",")]
         self.tc_max_rows = 256
+        # B200_TAIL=mega: in decode steps of up to 256 rows on one GPU, everything between two attention kernels
+        # (o_proj, add+norm, gate_up+SiluAndMul, down_proj, add+norm, the next layer's qkv_proj) is ONE persistent launch
+        # (csrc/layer_tail.cu) instead of seven
+        self.mega_tail = os.environ.get("B200_TAIL", "") == "mega" and tp_size == 1
+        self.mega_rows = 256
+        want = [int(v) for v in os.environ.get("B200_TAIL_SPLITS", "8,8").split(",")]
+        fit = lambda k, s: next(d for d in range(min(s, k // 64), 0, -1) if (k // 64) % d == 0)     # split-K factors must divide the k tiles
+        self.mega_splits = [fit(self.q_size, want[0]), fit(self.inter, want[1])] if self.q_size % 64 == 0 and self.inter % 64 == 0 else [1, 1]
+        self._tail_ws = None
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
         theta = getattr(c, "rope_theta", 1000000.0)
@@ -180,10 +189,46 @@ class Qwen3ForCausalLM:
             dist.all_reduce(h)
         return ops.add_rmsnorm(h, residual, weight, self.eps)
 
+    def _attention(self, li: int, qkv: torch.Tensor, positions: torch.Tensor, ctx):
+        """q/k-norm + RoPE + KV append + attention on the raw qkv projection (one or two launches) -> [t, q_size]."""
+        L, attn = self.layers[li], self.attn[li]
+        hq, hkv, d, t = self.num_heads, self.num_kv_heads, self.head_dim, qkv.shape[0]
+        cached = attn.k_cache.numel() > 0
+        if cached and not ctx.is_prefill and t <= self.fused_decode_max_batch:
+            o = ops.paged_decode_fused(li, qkv, hq, L.q_norm, L.k_norm, self.cos_sin, self.eps, ctx.block_tables,
+                                       ctx.context_lens, attn.scale)
+        else:
+            ops.qknorm_rope_store(li, qkv, hq, hkv, positions, L.q_norm, L.k_norm, self.cos_sin, self.eps,
+                                  ctx.slot_mapping if cached else None)
+            q = qkv[:, :self.q_size].view(t, hq, d)
+            k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
+            v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
+            o = attn(q, k, v, kv_stored=True)
+        return o.reshape(t, self.q_size)
+
+    def _forward_mega(self, input_ids: torch.Tensor, positions: torch.Tensor, ctx) -> torch.Tensor:
+        """Decode step with two launches per layer: attention, then the persistent layer tail (which also produces the
+        next layer's qkv projection)."""
+        if self._tail_ws is None:
+            self._tail_ws = ops.layer_tail_workspace(self.mega_rows, self.hidden, self.inter, max(self.mega_splits), self.device)
+        residual = ops.embedding(input_ids, self.embed)
+        x = ops.rmsnorm(residual, self.layers[0].ln1, self.eps)
+        qkv = F.linear(x, self.layers[0].qkv)
+        n = len(self.layers)
+        for li, L in enumerate(self.layers):
+            o = self._attention(li, qkv, positions, ctx)
+            nxt = self.layers[li + 1] if li + 1 < n else None
+            x, qkv = ops.layer_tail(o, residual, L.o, L.ln2, L.gate_up, L.down, nxt.ln1 if nxt is not None else self.norm, self.eps,
+                                    self._tail_ws, w_qkv_next=nxt.qkv if nxt is not None else None,
+                                    splits_o=self.mega_splits[0], splits_down=self.mega_splits[1])
+        return x
+
     @torch.inference_mode()
     def forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         ctx = get_context()
         eps, hq, hkv, d = self.eps, self.num_heads, self.num_kv_heads, self.head_dim
+        if self.mega_tail and not ctx.is_prefill and input_ids.shape[0] <= self.mega_rows and self.attn[0].k_cache.numel() > 0:
+            return self._forward_mega(input_ids, positions, ctx)
         h = ops.embedding(input_ids, self.embed)
         residual, in_peer = None, False
         cfg = self.tc_cfg

@@ -295,3 +295,49 @@ def lm_head_sample(hidden: torch.Tensor, lm_head: torch.Tensor, temperatures: to
                                       key_workspace.data_ptr(), _ptr(out), _ptr(out_keys), block_n, flags, _stream()))
     LAUNCHES[0] += 1                      # two kernels behind one call
     return out if out is not None else out_keys
+
+
+# ---- the tail of a decoder layer as one persistent kernel (csrc/layer_tail.cu) ---------------------------------------------
+def layer_tail_workspace(max_rows: int, hidden: int, inter: int, max_splits: int, device="cuda") -> torch.Tensor:
+    """Zeroed workspace (grid-barrier state, split-K partials, the two intermediate activations)."""
+    lib = nat.load()
+    n = lib.b200_layer_tail_workspace_bytes(max_rows, hidden, inter, max_splits)
+    if n == 0:
+        raise nat.B200Error("bad layer-tail workspace dimensions")
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def layer_tail(attn_out: torch.Tensor, residual: torch.Tensor, w_o: torch.Tensor, ln_mid: torch.Tensor, w_gate_up: torch.Tensor,
+               w_down: torch.Tensor, ln_next: torch.Tensor, eps: float, workspace: torch.Tensor, w_qkv_next: torch.Tensor | None = None,
+               splits_o: int = 8, splits_down: int = 8, x_next: torch.Tensor | None = None, qkv_out: torch.Tensor | None = None):
+    """o_proj -> add+RMSNorm -> gate_up+SiluAndMul -> down_proj -> add+RMSNorm [-> next qkv_proj] in ONE launch.
+    ``residual`` is updated in place; returns (x_next, qkv_out or None)."""
+    _need(attn_out, torch.bfloat16, "attn_out"); _need(residual, torch.bfloat16, "residual")
+    for t, name in ((w_o, "w_o"), (w_gate_up, "w_gate_up"), (w_down, "w_down"), (ln_mid, "ln_mid"), (ln_next, "ln_next")):
+        _need(t, torch.bfloat16, name)
+        assert t.is_contiguous()
+    assert attn_out.dim() == 2 and attn_out.stride(1) == 1 and residual.is_contiguous()
+    rows, q_size = attn_out.shape
+    hidden = residual.shape[1]
+    inter = w_down.shape[1]
+    assert w_o.shape == (hidden, q_size) and w_gate_up.shape == (2 * inter, hidden) and w_down.shape == (hidden, inter)
+    if x_next is None:
+        x_next = torch.empty_like(residual)
+    qkv_n = 0
+    if w_qkv_next is not None:
+        _need(w_qkv_next, torch.bfloat16, "w_qkv_next")
+        assert w_qkv_next.is_contiguous() and w_qkv_next.shape[1] == hidden
+        qkv_n = w_qkv_next.shape[0]
+        if qkv_out is None:
+            qkv_out = torch.empty(rows, qkv_n, dtype=torch.bfloat16, device=residual.device)
+    h = nat.handle()
+    nat.check(h.lib.b200_layer_tail(h.ptr, attn_out.data_ptr(), attn_out.stride(0), residual.data_ptr(), w_o.data_ptr(), ln_mid.data_ptr(),
+                                    w_gate_up.data_ptr(), w_down.data_ptr(), ln_next.data_ptr(), x_next.data_ptr(), _ptr(w_qkv_next),
+                                    _ptr(qkv_out), qkv_out.stride(0) if qkv_out is not None else 0, qkv_n, workspace.data_ptr(),
+                                    workspace.numel(), rows, hidden, q_size, inter, eps, splits_o, splits_down, _stream()), h.ptr)
+    return x_next, qkv_out
+
+
+def layer_tail_error(workspace: torch.Tensor) -> bool:
+    """True if a grid barrier of some launch on this workspace gave up waiting (results of that launch are undefined)."""
+    return int(workspace[8:12].view(torch.int32).item()) != 0

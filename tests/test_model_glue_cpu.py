@@ -129,6 +129,24 @@ class CpuOps:
         return y, residual
 
 
+    # ---- persistent layer tail (csrc/layer_tail.cu) ------------------------------------------------------------------
+    def layer_tail_workspace(self, max_rows, hidden, inter, max_splits, device="cpu"):
+        self._count("layer_tail_workspace")
+        return torch.zeros(16, dtype=torch.uint8)
+
+    def layer_tail(self, attn_out, residual, w_o, ln_mid, w_gate_up, w_down, ln_next, eps, workspace, w_qkv_next=None,
+                   splits_o=8, splits_down=8, x_next=None, qkv_out=None):
+        self._count("layer_tail")
+        import torch.nn.functional as F
+        assert attn_out.dim() == 2 and attn_out.stride(1) == 1 and residual.is_contiguous()
+        assert (attn_out.shape[1] // 64) % splits_o == 0 and (w_down.shape[1] // 64) % splits_down == 0
+        x, r = add_rmsnorm_ref(F.linear(attn_out, w_o), residual, ln_mid, eps)
+        h = F.linear(silu_mul_ref(F.linear(x, w_gate_up)), w_down)
+        xn, r = add_rmsnorm_ref(h, r, ln_next, eps)
+        residual.copy_(r)                                     # updated in place, like the kernel
+        return xn, (F.linear(xn, w_qkv_next) if w_qkv_next is not None else None)
+
+
 def run_product_model(monkeypatch, preset, env, fused_decode_max=None):
     import nanovllm.layers.attention as attn_mod
     import nanovllm.models.qwen3 as model_mod
@@ -185,6 +203,18 @@ def test_two_kernel_decode_path_glue(monkeypatch):
     for g, w in zip(got, want):
         assert torch.equal(g, w)
     assert fake.calls.get("paged_decode", 0) > 0 and "paged_decode_fused" not in fake.calls
+
+
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
+def test_mega_tail_path_glue_is_the_oracle(preset, monkeypatch):
+    """B200_TAIL=mega: decode steps run attention + ONE layer-tail op per layer; the glue (which norm weight, which next
+    qkv weight, residual in place, the last layer) must reproduce the oracle bit for bit when the op is exact."""
+    got, want, fake, model = run_product_model(monkeypatch, preset, {"B200_LINEAR": "cublas", "B200_TAIL": "mega"})
+    assert model.mega_tail
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert torch.equal(g, w), f"step {i}: max diff {(g.float() - w.float()).abs().max().item()}"
+    decode_steps = 3                                           # steps 1, 2 and 6 of the script
+    assert fake.calls["layer_tail"] == decode_steps * model.cfg.num_hidden_layers
 
 
 @pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
