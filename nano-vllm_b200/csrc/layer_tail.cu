@@ -97,7 +97,7 @@ __device__ __forceinline__ void grid_wait(const LtParams& p, unsigned int base, 
     const unsigned int target = base + (unsigned int)index + 1u;
     const long long t0 = clock64();
     while ((int)(ld_acquire_gpu(p.bar_gen) - target) < 0) {
-        if (clock64() - t0 > (1ll << 33)) {
+        if (clock64() - t0 > (1ll << 32)) {
             if (p.err) atomicExch(p.err, 1);
             break;
         }
@@ -171,9 +171,13 @@ layer_tail_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + LT_OFF_BAR + 144);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned int gen0 = ld_acquire_gpu(p.bar_gen);       // before this CTA's first arrival: no barrier of this launch can be complete
+    volatile uint32_t* gen_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + LT_OFF_BAR + 152);
 
     if (tid == 0) {
+        // the barrier generation at kernel entry, read ONCE per CTA before the set-up __syncthreads (hence before this
+        // CTA's first arrival, so no barrier of this launch can have completed) and shared through smem: a thread that
+        // read it on its own, later, could already see barrier 0 completed and would wait for one barrier too many
+        *gen_slot = ld_acquire_gpu(p.bar_gen);
         for (int i = 0; i < 2 * LT_STAGES; ++i) mbar_init(bars + i * 8, 1);
         mbar_init(bar_acc_full, 1);
         mbar_init(bar_acc_empty, 4);                           // one arrival per epilogue warp
@@ -187,6 +191,7 @@ layer_tail_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const unsigned int gen0 = *gen_slot;
 
     const CUtensorMap* const mx[4] = {&tm_x0, &tm_x1, &tm_x2, &tm_x3};
     const CUtensorMap* const mw[4] = {&tm_w0, &tm_w1, &tm_w2, &tm_w3};

@@ -11,3 +11,5 @@ B200ATTN_LIB=$PDL_LIB timeout 300 python profiles/step_time.py > $O/c3_step_pdl.
 B200_LM_HEAD=fused timeout 300 python profiles/step_time.py > $O/c3_step_fused_head.json 2> $O/c3_step_fused_head.err
 B200_FUSED_DECODE_MAX=256 timeout 300 python profiles/step_time.py > $O/c3_step_fuseddec256.json 2> $O/c3_step_fuseddec256.err
 cat $O/c3_step_*.json
+# (appended while queueing) the layer-tail kernel's first run
+bash profiles/r02_call4.sh
