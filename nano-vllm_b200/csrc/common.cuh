@@ -182,11 +182,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Programmatic dependent launch, compiled in only with -DB200_PDL (make PDL=1 -> libb200attn_pdl.so; staged, never
-// run on a GPU).  Without the define both macros expand to exactly what the sources said before: the default
-// library's SASS is unchanged.  With it every kernel starts with launch_dependents + wait (a no-op for a launch
+// Programmatic dependent launch, compiled in with -DB200_PDL (the Makefile's default; `make NOPDL=1` builds the plain
+// flavour as libb200attn_nopdl.so).  With it every kernel starts with launch_dependents + wait (a no-op for a launch
 // without the attribute) and every launch carries cudaLaunchAttributeProgrammaticStreamSerialization, so inside a
-// captured step the next kernel's blocks are scheduled while the previous kernel drains.
+// captured step the next kernel's blocks are scheduled while the previous kernel drains; kernels with a host-metadata
+// prologue (the decode attention kernels) wait only after it.  Without the define both macros expand to nothing / a
+// plain <<<>>> launch.  Measured on a B200 (profiles/r02_step_times.json): 2-5 % off every decode step.
 // ------------------------------------------------------------------------------------------
 #define B200_UNPAREN(...) __VA_ARGS__
 #ifdef B200_PDL

@@ -312,7 +312,12 @@ layer_tail_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
             // writer orders its own plain stores before later async-proxy (TMA) reads of them by other SMs.
             asm volatile("fence.proxy.async;" ::: "memory");
             epi_sync();
-            if (tid == 0) grid_arrive(p);
+            // A CTA never arrives at barrier k+1 before barrier k has completed: the arrival counter is reset by the
+            // last arriver of k, and an early arrival for k+1 could fall between its last increment and that reset.
+            if (tid == 0) {
+                if (next_barrier > 0) grid_wait(p, gen0, next_barrier - 1);
+                grid_arrive(p);
+            }
             const int b_written = next_barrier++;
             if (ph == 0 || ph == 2) {
                 if (tid == 0) grid_wait(p, gen0, b_written);
@@ -320,7 +325,7 @@ layer_tail_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
                 norm_rows(p, g.splits, ph == 0 ? p.ln_mid : p.ln_next, ph == 0 ? p.xbuf : p.x_next, warp, lane);
                 asm volatile("fence.proxy.async;" ::: "memory");
                 epi_sync();
-                if (tid == 0) grid_arrive(p);
+                if (tid == 0) grid_arrive(p);                   // barrier b_written has completed (waited for above)
                 next_barrier++;
             }
         }

@@ -76,14 +76,24 @@ class Qwen3ForCausalLM:
         if "B200_FUSED_DECODE_MAX" in os.environ and self.fused_decode_max_batch:      # tuning knob (e.g. under TP)
             self.fused_decode_max_batch = int(os.environ["B200_FUSED_DECODE_MAX"])
         self.peer = None        # engine/peer_reduce.PeerReduce when tensor parallel over NVLink peer memory
-        # Staged for the next round and OFF by default: B200_LINEAR=tc routes the decode-size projections through
-        # csrc/linear_tc.cu (tcgen05, SiluAndMul / split-K add+RMSNorm fused) instead of cuBLAS.  That kernel has not
-        # run on a GPU yet.  B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
-        mode = os.environ.get("B200_LINEAR", "cublas")
-        self.tc_linear = mode in ("tc", "rows")
-        self.tc_cols = mode == "tc"               # "rows": only the row-parallel o_proj / down_proj (split-K + fused add-norm)
-        self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,0").split(",")]
-        self.tc_max_rows = 256
+        # Decode-size projections (measured per batch size on a B200, profiles/r02_step_times.json, r02_linear_microbench.json):
+        #   B200_LINEAR=auto (default): the two row-parallel projections (o_proj, down_proj) of decode steps of up to 128 rows
+        #       run on tcgen05 with split-K 8 and the add+RMSNorm that follows consumes the fp32 partials in split order
+        #       (csrc/linear_tc.cu): 4-21 % off the step at batch <= 128; at batch 256 and for the wide projections
+        #       (qkv, gate_up) the library GEMM is faster, so those stay cuBLAS, as under tensor parallelism;
+        #   cublas: every projection through the library;  rows / tc: force the tcgen05 path for o/down / all four.
+        #   B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
+        mode = os.environ.get("B200_LINEAR", "auto")
+        self.tc_linear = mode in ("tc", "rows") or (mode == "auto" and tp_size == 1)
+        self.tc_cols = mode == "tc"               # "rows"/"auto": only the row-parallel o_proj / down_proj
+        self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,1").split(",")]
+        self.tc_max_rows = int(os.environ.get("B200_LINEAR_MAX_ROWS", "128" if mode == "auto" else "256"))
+        fit = lambda k, s: next(d for d in range(max(1, min(s, k // 64)), 0, -1) if (k // 64) % d == 0)     # split-K factors must divide the k tiles
+        tcc = self.tc_cfg
+        if self.q_size % 64 or self.inter % 64 or self.hidden % tcc[2] or self.hidden % tcc[4]:
+            self.tc_linear = False                # shapes the tcgen05 kernel does not tile: library GEMMs
+        else:
+            tcc[3], tcc[5] = fit(self.q_size, tcc[3]), fit(self.inter, tcc[5])
         # B200_TAIL=mega: in decode steps of up to 256 rows on one GPU, everything between two attention kernels
         # (o_proj, add+norm, gate_up+SiluAndMul, down_proj, add+norm, the next layer's qkv_proj) is ONE persistent launch
         # (csrc/layer_tail.cu) instead of seven

@@ -7,9 +7,8 @@ timeout 900 python -m pytest tests/test_gpu_tp.py -m gpu -q > $O/tp2_tests.log 2
 timeout 600 $TR --master-port 29601 bench.py --gpus 2 --steps 2 --warmup 2 > $O/tp2_bench_peer.json 2> $O/tp2_bench_peer.err
 B200_TP_ALLREDUCE=nvls timeout 600 $TR --master-port 29602 bench.py --gpus 2 --steps 2 --warmup 2 > $O/tp2_bench_nvls.json 2> $O/tp2_bench_nvls.err
 B200_TP_ALLREDUCE=nccl timeout 600 $TR --master-port 29603 bench.py --gpus 2 --steps 2 --warmup 2 --no-parity > $O/tp2_bench_nccl.json 2> $O/tp2_bench_nccl.err
-PDL_LIB=$PWD/nano-vllm_b200/lib/libb200attn_pdl.so
-B200ATTN_LIB=$PDL_LIB B200_LINEAR=tc B200_LINEAR_CFG=64,64,64,8,64,8,1 timeout 600 $TR --master-port 29604 bench.py --gpus 2 --steps 2 --warmup 2 > $O/tp2_bench_tc_pdl.json 2> $O/tp2_bench_tc_pdl.err
-tail -3 $O/tp2_tests.log; for f in peer nvls nccl tc_pdl; do python - $O/tp2_bench_$f.json <<'PY'
+B200_LINEAR=rows timeout 600 $TR --master-port 29604 bench.py --gpus 2 --steps 2 --warmup 2 > $O/tp2_bench_rows.json 2> $O/tp2_bench_rows.err
+tail -3 $O/tp2_tests.log; for f in peer nvls nccl rows; do python - $O/tp2_bench_$f.json <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[1], round(d['value']), round(d['e2e']['value']), d.get('parity'), d['notes'].get('host_loop'))

@@ -29,14 +29,14 @@ def test_exports_match_header():
     assert set(nat.SIGNATURES) == set(names), "ctypes table and header disagree"
 
 
-def test_pdl_flavour_exports_the_same_abi():
-    """`make PDL=1` (programmatic dependent launch compiled in; staged) must stay a drop-in for the default library."""
-    pdl = nat.lib_path().with_name("libb200attn_pdl.so")
+def test_plain_flavour_exports_the_same_abi():
+    """`make NOPDL=1` (the same sources without programmatic dependent launch) must stay a drop-in for the default library."""
+    pdl = nat.lib_path().with_name("libb200attn_nopdl.so")
     if not pdl.exists():
-        pytest.skip("PDL flavour not built (make -C nano-vllm_b200/csrc PDL=1)")
+        pytest.skip("plain flavour not built (make -C nano-vllm_b200/csrc NOPDL=1)")
     lib = ctypes.CDLL(str(pdl))
     for n in declared_symbols():
-        assert hasattr(lib, n), f"{n} missing from the PDL flavour"
+        assert hasattr(lib, n), f"{n} missing from the plain flavour"
     assert lib.b200_abi_version() == 2
 
 

@@ -276,3 +276,17 @@ def test_fused_lm_head_runner_glue(monkeypatch):
     assert seen == dict(rows=2, seed=3, step=0, step_dev=step_dev, offset=0)
     want = (hidden_all[[3, 9]].float() @ head.float().t()).argmax(-1)
     assert torch.equal(runner.g_tokens[:2], want)
+
+
+@pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
+def test_default_auto_linear_policy_glue(preset, monkeypatch):
+    """The default policy (B200_LINEAR=auto): o_proj / down_proj of small batches through the split-K tcgen05 path with the
+    fused add-norm, qkv / gate_up through the library; only the summation order differs from the oracle."""
+    monkeypatch.delenv("B200_LINEAR", raising=False)
+    got, want, fake, model = run_product_model(monkeypatch, preset, {})
+    assert model.tc_linear and not model.tc_cols and model.tc_max_rows == 128
+    assert fake.calls.get("linear2", 0) > 0 and fake.calls.get("add_rmsnorm_partials", 0) > 0
+    assert "linear0" not in fake.calls and "linear1" not in fake.calls and fake.calls.get("silu_mul", 0) > 0
+    for i, (g, w) in enumerate(zip(got, want)):
+        rel = ((g.float() - w.float()).norm() / w.float().norm()).item()
+        assert rel < 1e-2, f"step {i}: relative L2 {rel}"
