@@ -49,27 +49,30 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
     __shared__ float red[4];
     __shared__ int s_epoch;
     const int row = blockIdx.x;
+    // epoch only advances when the LAST CTA of a launch has passed its wait, so every thread of every CTA reads the same value
+    const int e = *reinterpret_cast<volatile int*>(epoch);
     if (threadIdx.x == 0) {
-        const int e = *reinterpret_cast<volatile int*>(epoch);
         s_epoch = e;
         if (blockIdx.x == 0) {
             __threadfence_system();                   // this rank's partials (previous kernel) before the announcement
             for (int p = 0; p < world; ++p)
                 if (p != rank) st_release_sys(reinterpret_cast<int*>(static_cast<uint8_t*>(bases[p]) + flag_off) + rank, e + 1);
         }
-        const int* mine = reinterpret_cast<const int*>(static_cast<const uint8_t*>(bases[rank]) + flag_off);
+    }
+    if (threadIdx.x < world && threadIdx.x != rank) {
+        // One thread per peer polls that peer's flag, so the system-scope acquire loads overlap instead of forming a chain of
+        // world-1 round trips in front of every exchange (56 exchanges per decode step).
         // A peer that never shows up (a rank died, a mis-wired handle) must not wedge the GPU: after 2^35 cycles
         // (~18 s, far beyond any skew between lock-stepped ranks) the launch gives up and raises *err; the
         // start-up self-test (engine/peer_reduce.py) then switches every rank to NCCL.
+        const int* mine = reinterpret_cast<const int*>(static_cast<const uint8_t*>(bases[rank]) + flag_off) + threadIdx.x;
         const long long t0 = clock64();
-        for (int p = 0; p < world; ++p)
-            if (p != rank)
-                while (ld_acquire_sys(mine + p) - (e + 1) < 0) {
-                    if (clock64() - t0 > (1ll << 35)) {
-                        if (err) atomicExch(err, 1);
-                        break;
-                    }
-                }
+        while (ld_acquire_sys(mine) - (e + 1) < 0) {
+            if (clock64() - t0 > (1ll << 35)) {
+                if (err) atomicExch(err, 1);
+                break;
+            }
+        }
     }
     __syncthreads();
 

@@ -35,9 +35,13 @@ class PeerReduce:
         torch.cuda.synchronize()
         self.handle = symm.rendezvous(self.raw, dist.group.WORLD)
         self.bases_dev = int(self.handle.buffer_ptrs_dev)
-        # B200_TP_ALLREDUCE=nvls (staged, opt-in): sum inside the NVSwitch through the multicast mapping, when there is one
+        # Sum inside the NVSwitch (multimem.ld_reduce on the multicast mapping of the same buffer) when there is a multicast
+        # mapping: every rank then pulls rows x hidden x 2 bytes per exchange instead of world x that.  Measured on B200
+        # (profiles/r02_bench_tp{2,8}_*.json): +3.7 % at 8 ranks, -2.5 % at 2 ranks, so the default (B200_TP_ALLREDUCE=auto)
+        # uses it from 4 ranks up; "peer" / "nvls" force one of the two, "nccl" bypasses this module.
         self.mc_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-        self.nvls = os.environ.get("B200_TP_ALLREDUCE", "peer") == "nvls" and self.mc_ptr != 0
+        mode = os.environ.get("B200_TP_ALLREDUCE", "auto")
+        self.nvls = self.mc_ptr != 0 and (mode == "nvls" or (mode == "auto" and world >= 4))
         self.state = torch.zeros(3, dtype=torch.int32, device=device)           # [epoch, done counter, error flag]
         self.views = [self.raw[i * self.buf_bytes:i * self.buf_bytes + rows_cap * hidden * 2].view(torch.bfloat16).view(rows_cap, hidden)
                       for i in range(2)]
@@ -54,7 +58,7 @@ class PeerReduce:
     @classmethod
     def create(cls, rows_cap, hidden, rank, world, device):
         """The workspace, or None -- decided unanimously -- when peer memory cannot be set up or fails its self-test."""
-        if os.environ.get("B200_TP_ALLREDUCE", "peer") not in ("peer", "nvls"):
+        if os.environ.get("B200_TP_ALLREDUCE", "auto") not in ("auto", "peer", "nvls"):
             return None
         obj, why = None, ""
         try:
