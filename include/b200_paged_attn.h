@@ -58,6 +58,11 @@ void b200_destroy(b200_ctx* ctx);
 const char* b200_strerror(int code);
 const char* b200_last_cuda_error(b200_ctx* ctx);
 int b200_sm_count(const b200_ctx* ctx);
+/* Per calling host thread: enabled == 0 makes every following launch of this library a plain stream-ordered launch
+ * (no programmatic-dependent-launch attribute) until it is enabled again; returns the previous setting.  No reference
+ * counterpart (the reference has no native launches): used around the kernels that follow a cross-stream event wait in
+ * the two-stream decode step.  A no-op in the library flavour built without PDL. */
+int b200_set_pdl(int enabled);
 /* ABI version of this header; bumped on any signature change. */
 int b200_abi_version(void);
 
@@ -206,8 +211,7 @@ int b200_sample(const void* logits, int logits_is_fp32, int64_t logits_stride0,
                 uint64_t seed, uint64_t step, const int64_t* step_dev, int64_t* out,
                 int64_t* out_keys, void* stream);
 
-/* ---- staged for the next round: compiled and exported, NOT yet run on a GPU, not on the product path -------------
- * (tests are opt-in: B200_EXPERIMENTAL=1 pytest tests/test_gpu_linear.py -m gpu)
+/* ---- decode-size projections on tcgen05 (validated on a B200 in round 2: tests/test_gpu_linear.py) ----------------
  *
  * F.linear of the reference's *ParallelLinear layers (layers/linear.py:51,73,153) for small batches, on tcgen05,
  * with what follows fused in (csrc/linear_tc.cu):

@@ -41,6 +41,12 @@ extern "C" const char* b200_last_cuda_error(b200_ctx* ctx) {
 
 extern "C" int b200_sm_count(const b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
+extern "C" int b200_set_pdl(int enabled) {
+    const int was = b200_tls_pdl_off() ? 0 : 1;
+    b200_tls_pdl_off() = (enabled == 0);
+    return was;
+}
+
 extern "C" int b200_kv_bind(b200_ctx* ctx, void* k_base, void* v_base, int layers,
                             int64_t num_blocks, int block_size, int num_kv_heads, int head_dim) {
     if (!ctx || !k_base || !v_base || layers <= 0 || num_blocks <= 0 || num_kv_heads <= 0) return B200_EINVAL;

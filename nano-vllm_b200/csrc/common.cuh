@@ -72,6 +72,12 @@ struct B200SmemOptIn {
         if (dev < 0 || dev >= B200_MAX_DEVICES) return cudaErrorInvalidDevice;
         if (done[dev]) return cudaSuccess;
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        // Ask for the largest shared-memory carve-out: a kernel of ANOTHER stream can only join this one on an SM if the
+        // SM's current L1/shared split already has room for both (the split is not changed under a running CTA).  The
+        // two-stream decode step (models/qwen3.py::_forward_dual) relies on it: tcgen05 projections of one half batch
+        // run in the ~73 KB that the attention kernel of the other half leaves free.  A hint; none of these kernels
+        // leans on L1.
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) done[dev] = true;
         return e;
     }
@@ -190,6 +196,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // plain <<<>>> launch.  Measured on a B200 (profiles/r02_step_times.json): 2-5 % off every decode step.
 // ------------------------------------------------------------------------------------------
 #define B200_UNPAREN(...) __VA_ARGS__
+// Per host thread: launches made while this is set carry NO programmatic-serialization attribute (b200_set_pdl).  Used for
+// the first kernel after a cross-stream event wait and for the kernel that follows an attention launch in the two-stream
+// decode step, where an early-launched dependent would sit on the shared memory the other stream's kernels need.
+inline bool& b200_tls_pdl_off() {
+    static thread_local bool off = false;
+    return off;
+}
 #ifdef B200_PDL
 #define B200_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define B200_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
@@ -209,7 +222,7 @@ static inline void b200_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 blo
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = b200_tls_pdl_off() ? 0 : 1;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through cudaGetLastError()
 }
 #define B200_LAUNCH(kernel_in_parens, grid, block, smem, stream, ...) \

@@ -1,9 +1,8 @@
 // Small-batch linear layers y = x W^T on the 5th-generation tensor cores, with the op that follows fused in.
 //
-// STATUS: staged for the next round.  This file compiles for sm_100a and is exported through the C ABI, but it has
-// not run on a GPU yet (the round's GPU budget was spent before it was written); nothing on the product path calls
-// it and its tests are opt-in (B200_EXPERIMENTAL=1).  It is assembled from the TMA / descriptor / tcgen05 idioms of
-// prefill_tc.cu, which are validated.
+// STATUS: validated on a B200 in round 2 (tests/test_gpu_linear.py, profiles/r02_linear_microbench.json).  On the product
+// path for o_proj / down_proj of decode batches <= 128 rows (split-K) and for all four projections of the two-stream decode
+// step (models/qwen3.py::_forward_dual), where a shallow ring lets these CTAs share an SM with the attention kernel.
 //
 // Why: in a decode step the four projections of a layer (reference layers/linear.py:51,73,153 -> F.linear -> cuBLAS)
 // take 5-7 us each whatever the batch is (profiles/README.md), 4-8x above the time their weights need to stream from
@@ -45,8 +44,9 @@ struct Cfg {
     static constexpr uint32_t W_TILE = BN * 128;
     static constexpr uint32_t STAGE = X_TILE + W_TILE;
     static constexpr int STAGES = !DEEP ? (BN <= 64 ? 4 : 3) : (BN <= 32 ? 8 : (BN <= 64 ? 6 : 4));
-    static constexpr uint32_t OFF_BAR = STAGES * STAGE;
-    static constexpr uint32_t SMEM = OFF_BAR + 256;          // full[S], empty[S], done, TMEM slot
+    static constexpr uint32_t SMEM = STAGES * STAGE + 256;   // ring, then full[S], empty[S], done, TMEM slot
+    // The ring depth actually used by a launch is LinParams::stages <= STAGES (b200_linear flags bits 4-7): the dynamic
+    // shared memory of that launch is stages * STAGE + 256, so a shallow launch fits beside another kernel's CTA.
     static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
@@ -56,6 +56,7 @@ struct LinParams {
     int rows;                 // M
     int up_row0;              // EPI_SILU: first W row of the "up" half (= inter)
     int k_tiles;              // 64-wide k tiles per split (gridDim.z splits)
+    int stages;               // ring slots of this launch (2 .. Cfg::STAGES)
     // EPI_SAMPLE (fused LM head + sampling): nothing of size [rows, vocab] is ever written
     int n_valid;                          // columns of this vocabulary shard (the last column block may be ragged)
     const float* temperatures;            // [rows] or null (greedy)
@@ -130,15 +131,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant
     using C = Cfg<BN, DEEP>;
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
     constexpr int X_ROWS = LM / CL;                            // rows of x this CTA fetches (and multicasts when CL > 1)
-    constexpr int S = C::STAGES;
+    const int S = p.stages;
     constexpr uint32_t IDESC = make_idesc(LM, BN, false);
     constexpr int BOUT = EPI == EPI_SILU ? BN / 2 : BN;       // output columns of this CTA
     extern __shared__ __align__(1024) uint8_t smem_raw[];     // 128-byte swizzle atoms need 1024-byte alignment
     const uint32_t base = smem_u32(smem_raw);
     if (base & 1023u) __trap();
-    const uint32_t bars = base + C::OFF_BAR;
+    const uint32_t off_bar = (uint32_t)S * C::STAGE;
+    const uint32_t bars = base + off_bar;
     const uint32_t bar_done = bars + 16 * S;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + C::OFF_BAR + 16 * S + 8);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + off_bar + 16 * S + 8);
 
     // let the next kernel of the stream start its own prologue (and weight prefetch) now; it still waits for this
     // grid to finish before it touches anything this grid writes (its own griddepcontrol.wait)
@@ -375,8 +377,10 @@ bool b200_cached_tensor_map(CUtensorMap* out, const void* base, uint64_t cols, u
 namespace {
 
 template <int BN, int EPI, bool DEEP, int CL>
-int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams& prm, dim3 grid, bool pdl, cudaStream_t stream) {
+int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, LinParams prm, dim3 grid, bool pdl, cudaStream_t stream) {
     using C = Cfg<BN, DEEP>;
+    if (prm.stages <= 0 || prm.stages > C::STAGES) prm.stages = C::STAGES;      // 0: this configuration's full ring
+    if (prm.stages < 2) prm.stages = 2;
     static B200SmemOptIn optin;
     if (cudaError_t e = optin.ensure(linear_tc_kernel<BN, EPI, DEEP, CL>, C::SMEM); e != cudaSuccess) {
         b200_tls_cuda_error() = cudaGetErrorString(e);
@@ -385,7 +389,7 @@ int launch_linear(const CUtensorMap& tx, const CUtensorMap& tw, const LinParams&
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(L_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.dynamicSmemBytes = (size_t)prm.stages * C::STAGE + 256;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -451,6 +455,7 @@ extern "C" int b200_linear(const void* x, int64_t x_stride0, const void* w, void
     prm.rows = rows;
     prm.up_row0 = n_out;
     prm.k_tiles = k_tiles_total / k_splits;
+    prm.stages = (flags >> 4) & 15;                                      // 0: the configuration's own depth
     dim3 grid(n_out / bout, (rows + LM - 1) / LM, k_splits);
     if (grid.y > 65535 || grid.z > 65535) return B200_EUNSUPPORTED;
     const bool pdl = (flags & 1) != 0;
@@ -490,6 +495,7 @@ extern "C" int b200_lm_head_sample(const void* hidden, int64_t hidden_stride0, c
     prm.step = step;
     prm.step_dev = step_dev;
     prm.keys = static_cast<unsigned long long*>(key_workspace);
+    prm.stages = (flags >> 4) & 15;
     dim3 grid(n_tiles, (rows + LM - 1) / LM, 1);
     if (grid.y > 65535) return B200_EUNSUPPORTED;
     const bool pdl = (flags & 1) != 0;

@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200_last_cuda_error": (C.c_char_p, [_vp]),
     "b200_sm_count": (_i, [_vp]),
     "b200_abi_version": (_i, []),
+    "b200_set_pdl": (_i, [_i]),
     "b200_kv_bind": (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _i]),
     "b200_decode_workspace_bytes": (_sz, [_vp, _i, _i]),
     "b200_store_kv": (_i, [_vp, _i, _vp, _i64, _vp, _i64, _vp, _i, _vp]),
@@ -36,7 +37,7 @@ SIGNATURES = {
     "b200_embedding": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp]),
     "b200_gather_tokens": (_i, [_vp, _vp, _vp, _i, _vp]),
     "b200_sample": (_i, [_vp, _i, _i64, _vp, _i, _i, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
-    # staged for the next round (csrc/linear_tc.cu): exported, never run on a GPU yet, not used by the engine
+    # decode-size projections on tcgen05 (csrc/linear_tc.cu) and the fused LM head / layer tail experiments
     "b200_linear": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200_add_rmsnorm_partials": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "b200_lm_head_sample": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _i, _i, _vp]),

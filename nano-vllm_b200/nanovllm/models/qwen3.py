@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import os
 from dataclasses import dataclass
+from types import SimpleNamespace
 
 import torch
 import torch.distributed as dist
@@ -103,6 +104,23 @@ class Qwen3ForCausalLM:
         fit = lambda k, s: next(d for d in range(min(s, k // 64), 0, -1) if (k // 64) % d == 0)     # split-K factors must divide the k tiles
         self.mega_splits = [fit(self.q_size, want[0]), fit(self.inter, want[1])] if self.q_size % 64 == 0 and self.inter % 64 == 0 else [1, 1]
         self._tail_ws = None
+        # Two-stream decode step (B200_DUAL, _forward_dual): a decode batch of >= dual_min rows is cut into two halves that
+        # run on two streams, half a layer out of phase: while one half is in its HBM-bound attention kernel (fp32-FMA pipe +
+        # bulk copies, ~155 KB of shared memory, one CTA per SM) the other half's latency-bound projection chain runs on
+        # the SAME SMs -- tcgen05 + TMA, a 3-slot ring (~72 KB) and ~10k registers, which is what the attention CTA leaves
+        # free.  Attention kernels never overlap each other (an event chain orders them), so HBM always has one streaming
+        # kernel and the chain of the other half hides under it.  One GPU, head groups <= 2 (the FMA decode kernel).
+        #   B200_DUAL_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,ring_slots"
+        dual = os.environ.get("B200_DUAL", "0")
+        self.dual = dual not in ("0", "", "off") and tp_size == 1 and self.num_heads // self.num_kv_heads <= 2
+        self.dual_min = int(os.environ.get("B200_DUAL_MIN", "144"))
+        self.dual_cfg = [int(v) for v in os.environ.get("B200_DUAL_CFG", "64,64,64,8,64,8,3").split(",")]
+        if self.q_size % 64 or self.inter % 64 or self.hidden % self.dual_cfg[2] or self.hidden % self.dual_cfg[4] \
+                or (self.q_size + 2 * self.kv_size) % self.dual_cfg[0] or self.inter % (self.dual_cfg[1] // 2):
+            self.dual = False
+        else:
+            self.dual_cfg[3], self.dual_cfg[5] = fit(self.q_size, self.dual_cfg[3]), fit(self.inter, self.dual_cfg[5])
+        self._dual_state = None
         if getattr(c, "attention_bias", False):
             raise NotImplementedError("qkv bias (Qwen2-style) is outside the Qwen3 hot path")
         theta = getattr(c, "rope_theta", 1000000.0)
@@ -199,21 +217,33 @@ class Qwen3ForCausalLM:
             dist.all_reduce(h)
         return ops.add_rmsnorm(h, residual, weight, self.eps)
 
-    def _attention(self, li: int, qkv: torch.Tensor, positions: torch.Tensor, ctx):
-        """q/k-norm + RoPE + KV append + attention on the raw qkv projection (one or two launches) -> [t, q_size]."""
+    def _attention(self, li: int, qkv: torch.Tensor, positions: torch.Tensor, ctx, before_attention=None, no_pdl: bool = False):
+        """q/k-norm + RoPE + KV append + attention on the raw qkv projection (one or two launches) -> [t, q_size].
+        ``before_attention`` runs right before the attention launch (cross-stream waits of the two-stream step);
+        ``no_pdl``: that launch carries no programmatic-dependent-launch attribute.  Decode steps only when either is used."""
+        import contextlib
         L, attn = self.layers[li], self.attn[li]
         hq, hkv, d, t = self.num_heads, self.num_kv_heads, self.head_dim, qkv.shape[0]
         cached = attn.k_cache.numel() > 0
+        plain = ops.pdl_off() if no_pdl else contextlib.nullcontext()
         if cached and not ctx.is_prefill and t <= self.fused_decode_max_batch:
-            o = ops.paged_decode_fused(li, qkv, hq, L.q_norm, L.k_norm, self.cos_sin, self.eps, ctx.block_tables,
-                                       ctx.context_lens, attn.scale)
+            if before_attention is not None:
+                before_attention()
+            with plain:
+                o = ops.paged_decode_fused(li, qkv, hq, L.q_norm, L.k_norm, self.cos_sin, self.eps, ctx.block_tables,
+                                           ctx.context_lens, attn.scale)
         else:
             ops.qknorm_rope_store(li, qkv, hq, hkv, positions, L.q_norm, L.k_norm, self.cos_sin, self.eps,
                                   ctx.slot_mapping if cached else None)
             q = qkv[:, :self.q_size].view(t, hq, d)
             k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
             v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
-            o = attn(q, k, v, kv_stored=True)
+            if before_attention is not None:
+                before_attention()
+                with plain:                                   # decode: the operator's decode branch, on this half's metadata
+                    o = ops.paged_decode(li, q, ctx.block_tables, ctx.context_lens, attn.scale)
+            else:
+                o = attn(q, k, v, kv_stored=True)
         return o.reshape(t, self.q_size)
 
     def _forward_mega(self, input_ids: torch.Tensor, positions: torch.Tensor, ctx) -> torch.Tensor:
@@ -233,10 +263,81 @@ class Qwen3ForCausalLM:
                                     splits_o=self.mega_splits[0], splits_down=self.mega_splits[1])
         return x
 
+    # ---- two-stream decode step ------------------------------------------------------------------
+    def _dual_streams(self):
+        """(main stream, side stream, one event per layer and half, fork/join events); CPU tensors (glue tests): no streams."""
+        if self.device.type != "cuda":
+            return None
+        if self._dual_state is None:
+            n = len(self.layers)
+            self._dual_state = (torch.cuda.Stream(self.device), [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(n)],
+                                torch.cuda.Event(), torch.cuda.Event())
+        return self._dual_state
+
+    def _forward_dual(self, input_ids: torch.Tensor, positions: torch.Tensor, ctx) -> torch.Tensor:
+        """Decode step as two half batches on two streams, half a layer out of phase (see __init__).  Per half and layer:
+        add+norm(split-K partials) -> qkv (tcgen05) -> attention [no PDL, after the other half's attention] -> o_proj split-K
+        [no PDL] -> add+norm -> gate_up+SiluAndMul (tcgen05) -> down_proj split-K.  Same rounding points as the single-stream
+        tcgen05 path (split-K partials summed in split order by the add+norm)."""
+        import contextlib
+        n = input_ids.shape[0]
+        h0 = (n + 1) // 2
+        cfg, eps = self.dual_cfg, self.eps
+        ring = cfg[6]
+        st = self._dual_streams()
+        hidden = ops.embedding(input_ids, self.embed)        # the residual stream of both halves, updated in place
+        out = torch.empty_like(hidden)
+        if st is not None:
+            side, events, ev_fork, ev_join = st
+            main = torch.cuda.current_stream()
+            ev_fork.record(main)
+            side.wait_event(ev_fork)
+            streams = (main, side)
+        halves = []
+        for k, (a, b) in enumerate(((0, h0), (h0, n))):
+            sub = SimpleNamespace(is_prefill=False, slot_mapping=ctx.slot_mapping[a:b] if ctx.slot_mapping is not None else None,
+                                  context_lens=ctx.context_lens[a:b], block_tables=ctx.block_tables[a:b])
+            halves.append(SimpleNamespace(a=a, b=b, residual=hidden[a:b], pos=positions[a:b], ctx=sub, parts=None))
+        last_attn = None                                      # event of the most recent attention launch (either half)
+        nl = len(self.layers)
+        for li, L in enumerate(self.layers):
+            for k, hb in enumerate(halves):
+                if hb.b == hb.a:
+                    continue
+                scope = torch.cuda.stream(streams[k]) if st is not None else contextlib.nullcontext()
+                with scope:
+                    if hb.parts is None:
+                        x = ops.rmsnorm(hb.residual, L.ln1, eps)
+                    else:
+                        x, _ = ops.add_rmsnorm_partials(hb.parts, hb.residual, L.ln1, eps, pdl=True)
+                    qkv = ops.linear(x, L.qkv, ops.EPI_BF16, cfg[0], pdl=True, stages=ring)
+
+                    def before_attention(k=k):
+                        if st is not None and last_attn is not None:
+                            streams[k].wait_event(last_attn)
+
+                    o = self._attention(li, qkv, hb.pos, hb.ctx, before_attention=before_attention, no_pdl=True)
+                    if st is not None:
+                        last_attn = events[li][k]
+                        last_attn.record(streams[k])
+                    # an early-launched dependent of the attention kernel would sit on the shared memory the other half needs
+                    parts = ops.linear(o, L.o, ops.EPI_PARTIAL, cfg[2], cfg[3], pdl=False, stages=ring)
+                    x, _ = ops.add_rmsnorm_partials(parts, hb.residual, L.ln2, eps, pdl=True)
+                    act = ops.linear(x, L.gate_up, ops.EPI_SILU, cfg[1], pdl=True, stages=ring)
+                    hb.parts = ops.linear(act, L.down, ops.EPI_PARTIAL, cfg[4], cfg[5], pdl=True, stages=ring)
+                    if li == nl - 1:
+                        ops.add_rmsnorm_partials(hb.parts, hb.residual, self.norm, eps, pdl=True, out=out[hb.a:hb.b])
+        if st is not None:
+            ev_join.record(side)
+            main.wait_event(ev_join)
+        return out
+
     @torch.inference_mode()
     def forward(self, input_ids: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
         ctx = get_context()
         eps, hq, hkv, d = self.eps, self.num_heads, self.num_kv_heads, self.head_dim
+        if self.dual and not ctx.is_prefill and input_ids.shape[0] >= self.dual_min and self.attn[0].k_cache.numel() > 0:
+            return self._forward_dual(input_ids, positions, ctx)
         if self.mega_tail and not ctx.is_prefill and input_ids.shape[0] <= self.mega_rows and self.attn[0].k_cache.numel() > 0:
             return self._forward_mega(input_ids, positions, ctx)
         h = ops.embedding(input_ids, self.embed)

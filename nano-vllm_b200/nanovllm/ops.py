@@ -237,14 +237,28 @@ def tokens_from_keys(keys: torch.Tensor) -> torch.Tensor:
     return 0xffffffff - (keys & 0xffffffff)
 
 
-# ---- staged for the next round (csrc/linear_tc.cu): not yet run on a GPU, not used by the engine ---------------------
+# ---- decode-size projections on tcgen05 (csrc/linear_tc.cu) -----------------------------------------------------------
 EPI_BF16, EPI_SILU, EPI_PARTIAL = 0, 1, 2
 
 
+class pdl_off:
+    """Context manager: launches inside carry no programmatic-dependent-launch attribute (b200_set_pdl)."""
+
+    def __enter__(self):
+        self._was = nat.load().b200_set_pdl(0)
+        return self
+
+    def __exit__(self, *exc):
+        nat.load().b200_set_pdl(self._was)
+        return False
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, block_n: int = 32, k_splits: int = 1,
-           pdl: bool = False, out: torch.Tensor | None = None, shallow: bool = False, cluster: int = 1) -> torch.Tensor:
+           pdl: bool = False, out: torch.Tensor | None = None, shallow: bool = False, cluster: int = 1,
+           stages: int = 0) -> torch.Tensor:
     """x [rows, k] @ w[n, k]^T on tcgen05.  EPI_SILU: w = [gate; up] rows, returns silu(gate) * up [rows, n/2];
-    EPI_PARTIAL: returns fp32 [k_splits, rows, n] partial sums for ``add_rmsnorm_partials``."""
+    EPI_PARTIAL: returns fp32 [k_splits, rows, n] partial sums for ``add_rmsnorm_partials``.
+    ``stages`` (0 = default): ring depth in slots of 16 KB + block_n * 128 B."""
     _need(x, torch.bfloat16, "x"); _need(w, torch.bfloat16, "w")
     assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.shape[1] == w.shape[1]
     rows, k = x.shape
@@ -257,7 +271,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, epilogue: int = EPI_BF16, block_n: 
     lib = nat.load()
     nat.check(lib.b200_linear(x.data_ptr(), x.stride(0), w.data_ptr(), out.data_ptr(), out.stride(-2), rows, n_out, k,
                               epilogue, block_n, k_splits,
-                              int(pdl) | (2 if shallow else 0) | ({1: 0, 2: 1, 4: 2}[cluster] << 2), _stream()))
+                              int(pdl) | (2 if shallow else 0) | ({1: 0, 2: 1, 4: 2}[cluster] << 2) | ((stages & 15) << 4),
+                              _stream()))
     return out
 
 

@@ -1,21 +1,14 @@
-"""Opt-in parity tests for the staged tcgen05 linear layer (csrc/linear_tc.cu).
-
-The kernel was written after this round's GPU budget was spent and has never run; an untested tensor-core kernel can
-hang as well as be wrong, so these tests only run when asked for:
-
-    B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_linear.py -m gpu -x -q
+"""Parity tests for the tcgen05 linear layer (csrc/linear_tc.cu): the decode-size projections of the product path (o_proj /
+down_proj split-K for batches <= 128 rows; all four in the two-stream decode step) and the fused LM-head + sampling kernel.
 
 Reference for every case: torch fp32 matmul of the same bf16 inputs, rounded where the reference rounds
 (F.linear output is bf16, layers/linear.py:51,73,153; SiluAndMul in fp32 on that, layers/activation.py:8-11).
+First run on a B200 in round 2 (all green); part of the default GPU suite since.
 """
-import os
-
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_EXPERIMENTAL") != "1",
-                                 reason="staged kernel, never run on a GPU: set B200_EXPERIMENTAL=1 to try it")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _inputs(rows, n, k, seed=0, x_pad=0):
@@ -47,6 +40,20 @@ def test_linear_shallow_ring(block_n):
     want = x.float() @ w.float().t()
     assert (got.float() - want).abs().max().item() <= 2.0 ** -7 * want.abs().max().item() + 1e-3
     assert torch.equal(got, ops.linear(x, w, ops.EPI_BF16, block_n))      # ring depth does not change the arithmetic
+
+
+@pytest.mark.parametrize("stages", [2, 3])
+@pytest.mark.parametrize("block_n", [32, 64])
+def test_linear_explicit_ring_depth(stages, block_n):
+    """flags bits 4-7: the 2-3 slot rings of the two-stream decode step (a CTA that fits beside the attention kernel's);
+    the ring depth changes the schedule, never the arithmetic."""
+    from nanovllm import ops
+    x, w = _inputs(128, 1024, 2048, seed=block_n + stages)
+    assert torch.equal(ops.linear(x, w, ops.EPI_BF16, block_n, stages=stages, pdl=True), ops.linear(x, w, ops.EPI_BF16, block_n))
+    xw, ww = _inputs(100, 2 * 3072, 1024, seed=7)
+    assert torch.equal(ops.linear(xw, ww, ops.EPI_SILU, block_n, stages=stages), ops.linear(xw, ww, ops.EPI_SILU, block_n))
+    xd, wd = _inputs(128, 1024, 3072, seed=8)
+    assert torch.equal(ops.linear(xd, wd, ops.EPI_PARTIAL, block_n, 8, stages=stages), ops.linear(xd, wd, ops.EPI_PARTIAL, block_n, 8))
 
 
 @pytest.mark.parametrize("cluster", [2, 4])

@@ -122,6 +122,36 @@ def test_engine_greedy_generate_vs_oracle(tiny_dir, eager):
     record("engine_greedy", dict(eager=eager, tokens=tot, differ_from_oracle_argmax=diff, worst_margin_over_tol=worst))
 
 
+@pytest.mark.parametrize("eager", [True, False])
+def test_engine_two_stream_decode_vs_oracle(tiny_dir, eager, monkeypatch):
+    """B200_DUAL=1: every decode step of >= 2 rows runs as two half batches on two streams (event chain between the two
+    attention launches, tcgen05 projections with a 3-slot ring, captured into the decode graphs when not eager); greedy
+    tokens teacher-forced against the oracle, and equal to the single-stream engine's wherever the oracle has a clear winner."""
+    from nanovllm import LLM, SamplingParams
+    from nanovllm.utils.synthetic import PRESETS, random_weights
+    monkeypatch.setenv("B200_DUAL", "1")
+    monkeypatch.setenv("B200_DUAL_MIN", "2")
+    llm = LLM(tiny_dir, enforce_eager=eager, max_model_len=256, max_num_seqs=8, max_num_batched_tokens=128,
+              kvcache_block_size=16, num_kvcache_blocks=64)
+    try:
+        assert llm.model_runner.model.dual
+        prompts = _prompts(PRESETS["tiny"]["vocab_size"])
+        sps = [SamplingParams(temperature=0.0, max_tokens=8 + (i % 5) * 6, ignore_eos=True) for i in range(len(prompts))]
+        outs = llm.generate(prompts, sps, use_tqdm=False)
+        again = llm.generate(prompts, sps, use_tqdm=False)             # replays of the same graphs / streams: deterministic
+    finally:
+        llm.exit()
+    assert [o["token_ids"] for o in outs] == [o["token_ids"] for o in again]
+    oracle = make_oracle(PRESETS["tiny"], random_weights(PRESETS["tiny"], seed=1234), "fused")
+    tot = diff = 0
+    worst = 0.0
+    for p, sp, o in zip(prompts, sps, outs):
+        assert len(o["token_ids"]) == sp.max_tokens
+        n, d, w = check_greedy_against_oracle(oracle, p, o["token_ids"])
+        tot, diff, worst = tot + n, diff + d, max(worst, w)
+    record("engine_two_stream", dict(eager=eager, tokens=tot, differ_from_oracle_argmax=diff, worst_margin_over_tol=worst))
+
+
 def test_engine_chunked_prefill_and_preemption(tiny_dir):
     """Prompts longer than max_num_batched_tokens (chunked prefill through the paged path) and a KV cache too small
     for the whole batch (preemption + re-prefill through the prefix cache), greedy, checked against the oracle."""

@@ -98,8 +98,20 @@ class CpuOps:
         store_kvcache_ref(k, v, self.kv[layer][0], self.kv[layer][1], slot_mapping)
 
     # ---- staged tcgen05 projections ---------------------------------------------------------------------------------
-    def linear(self, x, w, epilogue=0, block_n=32, k_splits=1, pdl=False, out=None, shallow=False, cluster=1):
+    class pdl_off:
+        depth = 0
+
+        def __enter__(self):
+            type(self).depth += 1
+            return self
+
+        def __exit__(self, *exc):
+            type(self).depth -= 1
+            return False
+
+    def linear(self, x, w, epilogue=0, block_n=32, k_splits=1, pdl=False, out=None, shallow=False, cluster=1, stages=0):
         self._count(f"linear{epilogue}")
+        assert 0 <= stages <= 8
         assert x.dim() == 2 and x.stride(1) == 1 and w.is_contiguous() and x.shape[1] == w.shape[1] and x.shape[1] % 64 == 0
         xf, wf = x.float(), w.float()
         if epilogue == self.EPI_PARTIAL:
@@ -121,11 +133,15 @@ class CpuOps:
     def add_rmsnorm_partials(self, partials, residual, weight, eps, pdl=False, out=None):
         self._count("add_rmsnorm_partials")
         assert partials.dtype == torch.float32 and partials.dim() == 3 and partials.shape[1:] == residual.shape
+        assert residual.is_contiguous() and (out is None or (out.is_contiguous() and out.shape == residual.shape))
         h = partials[0].clone()
         for s in range(1, partials.shape[0]):
             h += partials[s]
         y, r = add_rmsnorm_ref(h.to(torch.bfloat16), residual, weight, eps)
         residual.copy_(r)
+        if out is not None:
+            out.copy_(y)
+            return out, residual
         return y, residual
 
 
@@ -226,6 +242,27 @@ def test_staged_tc_linear_path_glue(preset, monkeypatch):
     assert fake.calls["linear0"] == layers * steps and fake.calls["linear1"] == layers * steps      # qkv, gate_up+silu
     assert fake.calls["linear2"] == 2 * layers * steps and fake.calls["add_rmsnorm_partials"] == 2 * layers * steps
     assert "silu_mul" not in fake.calls and "add_rmsnorm" not in fake.calls
+    for i, (g, w) in enumerate(zip(got, want)):
+        rel = ((g.float() - w.float()).norm() / w.float().norm()).item()
+        assert rel < 1e-2, f"step {i}: relative L2 {rel}"
+
+
+@pytest.mark.parametrize("preset,fused_max", [("tiny", None), ("tiny", 0)])
+def test_two_stream_decode_path_glue(preset, fused_max, monkeypatch):
+    """B200_DUAL=1: decode batches are cut into two halves (streams on the GPU; plain order here) that each run the tcgen05
+    chain on their own rows / block tables / context lengths; the result must be the single-stream tcgen05 result (only
+    the split-K summation order differs from the oracle)."""
+    got, want, fake, model = run_product_model(monkeypatch, preset, {"B200_DUAL": "1", "B200_DUAL_MIN": "2", "B200_LINEAR": "cublas",
+                                                                    "B200_DUAL_CFG": "32,32,64,4,64,4,3"}, fused_decode_max=fused_max)
+    assert model.dual and model.dual_min == 2
+    layers = model.cfg.num_hidden_layers
+    assert fake.calls.get("linear2", 0) >= 2 * 2 * layers           # o/down split-K partials of both halves of >= 1 decode step
+    assert fake.calls.get("linear1", 0) >= 2 * layers and fake.calls.get("linear0", 0) >= 2 * layers
+    assert fake.pdl_off.depth == 0
+    if fused_max == 0:
+        assert fake.calls.get("paged_decode", 0) > 0
+    else:
+        assert fake.calls.get("paged_decode_fused", 0) > 0
     for i, (g, w) in enumerate(zip(got, want)):
         rel = ((g.float() - w.float()).norm() / w.float().norm()).item()
         assert rel < 1e-2, f"step {i}: relative L2 {rel}"
