@@ -89,12 +89,16 @@ class Qwen3ForCausalLM:
         self.tc_cols = mode == "tc"               # "rows"/"auto": only the row-parallel o_proj / down_proj
         self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,1").split(",")]
         self.tc_max_rows = int(os.environ.get("B200_LINEAR_MAX_ROWS", "128" if mode == "auto" else "256"))
+        # above 128 rows a CTA row block is added, so fewer k splits cover the SMs (micro-benchmark at 256 rows, split 4 vs 8:
+        # o_proj 7.6 vs 11.2 us, down_proj 8.8 vs 12.5 us incl. the add-norm); B200_LINEAR_SPLITS_BIG overrides
+        self.tc_big_splits = int(os.environ.get("B200_LINEAR_SPLITS_BIG", "4"))
         fit = lambda k, s: next(d for d in range(max(1, min(s, k // 64)), 0, -1) if (k // 64) % d == 0)     # split-K factors must divide the k tiles
         tcc = self.tc_cfg
         if self.q_size % 64 or self.inter % 64 or self.hidden % tcc[2] or self.hidden % tcc[4]:
             self.tc_linear = False                # shapes the tcgen05 kernel does not tile: library GEMMs
         else:
             tcc[3], tcc[5] = fit(self.q_size, tcc[3]), fit(self.inter, tcc[5])
+            self.tc_big = (fit(self.q_size, min(tcc[3], self.tc_big_splits)), fit(self.inter, min(tcc[5], self.tc_big_splits)))
         # B200_TAIL=mega: in decode steps of up to 256 rows on one GPU, everything between two attention kernels
         # (o_proj, add+norm, gate_up+SiluAndMul, down_proj, add+norm, the next layer's qkv_proj) is ONE persistent launch
         # (csrc/layer_tail.cu) instead of seven
@@ -365,13 +369,14 @@ class Qwen3ForCausalLM:
                 k = qkv[:, self.q_size:self.q_size + self.kv_size].view(t, hkv, d)
                 v = qkv[:, self.q_size + self.kv_size:].view(t, hkv, d)
                 o = attn(q, k, v, kv_stored=True)
-            h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o, (cfg[2], cfg[3]) if tc else None)
+            big = tc and t > 128
+            h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o, (cfg[2], self.tc_big[0] if big else cfg[3]) if tc else None)
             x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln2)
             if tc and self.tc_cols:
                 act = ops.linear(x, L.gate_up, ops.EPI_SILU, cfg[1], pdl=bool(cfg[6]))
             else:
                 act = ops.silu_mul(F.linear(x, L.gate_up))
-            h, in_peer = self._row_linear(act, L.down, (cfg[4], cfg[5]) if tc else None)
+            h, in_peer = self._row_linear(act, L.down, (cfg[4], self.tc_big[1] if big else cfg[5]) if tc else None)
         x, _ = self._reduce_add_norm(h, in_peer, residual, self.norm)
         return x
 
