@@ -51,13 +51,14 @@ __global__ void __launch_bounds__(AR_THREADS) allreduce_add_rmsnorm_kernel(
     const int row = blockIdx.x;
     // epoch only advances when the LAST CTA of a launch has passed its wait, so every thread of every CTA reads the same value
     const int e = *reinterpret_cast<volatile int*>(epoch);
-    if (threadIdx.x == 0) {
-        s_epoch = e;
-        if (blockIdx.x == 0) {
-            __threadfence_system();                   // this rank's partials (previous kernel) before the announcement
-            for (int p = 0; p < world; ++p)
-                if (p != rank) st_release_sys(reinterpret_cast<int*>(static_cast<uint8_t*>(bases[p]) + flag_off) + rank, e + 1);
-        }
+    if (threadIdx.x == 0) s_epoch = e;
+    if (blockIdx.x == 0 && threadIdx.x < world && threadIdx.x != rank) {
+        // Announce to every peer AT ONCE, one thread per peer: a release store at system scope cannot complete before the
+        // writes ahead of it are performed, so a loop of world-1 of them in one thread is a chain of world-1 NVLink round
+        // trips in front of every exchange (the reason 8 ranks were slower than 4).  Each thread orders this rank's
+        // partials (previous kernel) before its own flag store.
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<int*>(static_cast<uint8_t*>(bases[threadIdx.x]) + flag_off) + rank, e + 1);
     }
     if (threadIdx.x < world && threadIdx.x != rank) {
         // One thread per peer polls that peer's flag, so the system-scope acquire loads overlap instead of forming a chain of
@@ -154,7 +155,7 @@ extern "C" int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t d
     return b200_launch_status(nullptr);
 }
 
-// Same exchange with the reduction done inside the NVSwitch (staged: not yet run on a GPU).  `multicast_base` is the
+// Same exchange with the reduction done inside the NVSwitch (default from 4 ranks; validated at 2, 4 and 8 ranks in round 2).  `multicast_base` is the
 // multicast mapping of the same symmetric allocation (torch symmetric memory: handle.multicast_ptr).
 extern "C" int b200_allreduce_add_rmsnorm_nvls(const void* peer_bases_dev, const void* multicast_base, uint64_t data_offset,
                                                uint64_t flag_offset, int* epoch, unsigned int* done, int* err_flag, int rank,

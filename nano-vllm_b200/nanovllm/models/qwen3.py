@@ -82,11 +82,14 @@ class Qwen3ForCausalLM:
         #       run on tcgen05 with split-K 8 and the add+RMSNorm that follows consumes the fp32 partials in split order
         #       (csrc/linear_tc.cu): 4-21 % off the step at batch <= 128; at batch 256 and for the wide projections
         #       (qkv, gate_up) the library GEMM is faster, so those stay cuBLAS, as under tensor parallelism;
-        #   cublas: every projection through the library;  rows / tc: force the tcgen05 path for o/down / all four.
+        #   cublas: every projection through the library;  rows / tc: force the tcgen05 path for o/down / all four;
+        #   gu: only gate_up + SiluAndMul on tcgen05 (one launch less per layer), the rest through the library.
         #   B200_LINEAR_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,pdl".
         mode = os.environ.get("B200_LINEAR", "auto")
         self.tc_linear = mode in ("tc", "rows") or (mode == "auto" and tp_size == 1)
         self.tc_cols = mode == "tc"               # "rows"/"auto": only the row-parallel o_proj / down_proj
+        self.tc_gate_up = mode == "gu" and self.inter % 32 == 0
+        self.tc_gate_up_max = int(os.environ.get("B200_LINEAR_GU_MAX_ROWS", "256"))
         self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,1").split(",")]
         self.tc_max_rows = int(os.environ.get("B200_LINEAR_MAX_ROWS", "128" if mode == "auto" else "256"))
         # above 128 rows a CTA row block is added, so fewer k splits cover the SMs (micro-benchmark at 256 rows, split 4 vs 8:
@@ -372,7 +375,7 @@ class Qwen3ForCausalLM:
             big = tc and t > 128
             h, in_peer = self._row_linear(o.reshape(t, self.q_size), L.o, (cfg[2], self.tc_big[0] if big else cfg[3]) if tc else None)
             x, residual = self._reduce_add_norm(h, in_peer, residual, L.ln2)
-            if tc and self.tc_cols:
+            if (tc and self.tc_cols) or (self.tc_gate_up and not ctx.is_prefill and t <= self.tc_gate_up_max):
                 act = ops.linear(x, L.gate_up, ops.EPI_SILU, cfg[1], pdl=bool(cfg[6]))
             else:
                 act = ops.silu_mul(F.linear(x, L.gate_up))
