@@ -268,6 +268,18 @@ def test_two_stream_decode_path_glue(preset, fused_max, monkeypatch):
         assert rel < 1e-2, f"step {i}: relative L2 {rel}"
 
 
+def test_gate_up_only_tc_mode_glue(monkeypatch):
+    """B200_LINEAR=gu: decode steps run gate_up + SiluAndMul as ONE tcgen05 op, every other projection stays a library call
+    (the mode tensor-parallel runs use to save a launch per layer); prefill keeps the two-op path."""
+    got, want, fake, model = run_product_model(monkeypatch, "tiny", {"B200_LINEAR": "gu"})
+    assert model.tc_gate_up and not model.tc_linear
+    layers, decode_steps = model.cfg.num_hidden_layers, 3
+    assert fake.calls["linear1"] == layers * decode_steps
+    assert "linear0" not in fake.calls and "linear2" not in fake.calls and fake.calls.get("silu_mul", 0) > 0
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert torch.equal(g, w), f"step {i}"            # the stand-in rounds exactly where the two-op path rounds
+
+
 def test_fused_lm_head_runner_glue(monkeypatch):
     """ModelRunner._forward_and_sample with B200_LM_HEAD=fused hands the right tensors to ops.lm_head_sample (staged path)."""
     import nanovllm.engine.model_runner as mr
