@@ -167,7 +167,7 @@ int b200_allreduce_add_rmsnorm(const void* peer_bases_dev, uint64_t data_offset,
                                void* residual, const void* weight, void* out, int rows, int cols, float eps,
                                void* stream);
 
-/* (staged, not yet run on a GPU) The same exchange with the sum taken inside the NVSwitch (NVLS): partials are read
+/* The same exchange with the sum taken inside the NVSwitch (NVLS; the engine's default from 4 ranks): partials are read
  * through `multicast_base`, the multicast mapping of the same symmetric allocation, with multimem.ld_reduce (fp32
  * accumulation in the switch, ONE rounding to bf16 -- the rounding point of the reference's bf16 all_reduce), so a
  * rank moves `rows x cols x 2` bytes instead of world times that.  Handshake, arguments and outputs as above, except
@@ -227,7 +227,7 @@ int b200_sample(const void* logits, int logits_is_fp32, int64_t logits_stride0,
 int b200_linear(const void* x, int64_t x_stride0, const void* w, void* out, int64_t out_stride0, int rows,
                 int n_out, int k, int epilogue, int block_n, int k_splits, int flags, void* stream);
 
-/* (staged) ParallelLMHead.forward + Sampler.forward in one pass (layers/embed_head.py:56-66, layers/sampler.py:7-12):
+/* (opt-in: parity-green, slower than the library GEMM + b200_sample) ParallelLMHead.forward + Sampler.forward in one pass (layers/embed_head.py:56-66, layers/sampler.py:7-12):
  * logits = bf16(hidden lm_head^T) are produced tile by tile in tensor memory, scored exactly as b200_sample scores
  * them (same RNG keyed by (seed, step, row, vocabulary id); temperature 0 = greedy, lowest index on ties) and
  * reduced to one packed (score, token) key per row with atomicMax -- the [rows, vocab] logits are never written.

@@ -391,7 +391,8 @@ class ModelRunner:
         """hidden -> shard logits -> sampled token ids in self.g_tokens[:rows] (all enqueued, no sync)."""
         hidden = self.model(input_ids, positions)
         if self.fused_lm_head and rows <= self.g_keyws.numel():
-            # staged, opt-in (B200_LM_HEAD=fused): LM head + sampling in one tensor-core kernel, logits never written
+            # opt-in (B200_LM_HEAD=fused): LM head + sampling in one tensor-core kernel, logits never written; parity-green but
+            # slower than the library GEMM + sample_kernel pair (DESIGN.md 3.4), hence not the default
             last = self.model.last_token_rows(hidden)
             if self.world_size == 1:
                 ops.lm_head_sample(last, self.model.lm_head, temps, self.sample_seed, 0, self.g_keyws, out=self.g_tokens[:rows],

@@ -200,7 +200,7 @@ class Qwen3ForCausalLM:
     # ---- forward -------------------------------------------------------------------------------
     def _row_linear(self, x: torch.Tensor, w: torch.Tensor, tc=None):
         """Row-parallel GEMM (o_proj / down_proj).  Returns (partial, where): where is True when the partial sits in
-        the peer-mapped buffer, "parts" when it is the fp32 split-K partials of the staged tcgen05 path."""
+        the peer-mapped buffer, "parts" when it is the fp32 split-K partials of the tcgen05 path."""
         peer = self.peer
         if tc is not None and self.tp_size == 1:
             return ops.linear(x, w, ops.EPI_PARTIAL, tc[0], tc[1], pdl=bool(self.tc_cfg[6])), "parts"

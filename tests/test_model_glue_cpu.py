@@ -1,7 +1,7 @@
 """The product's model code (nanovllm/models/qwen3.py) with every GPU op replaced by a CPU stand-in built from the
 oracle's free functions: checks the PYTHON around the kernels -- which op is called when, with which views, strides,
 argument order and return values -- without a GPU.  On the default path the stand-ins are the oracle's own arithmetic,
-so the logits must equal the oracle's bit for bit; on the staged paths (B200_LINEAR=tc: tcgen05 projections with fused
+so the logits must equal the oracle's bit for bit; on the tcgen05 paths (B200_LINEAR=tc: tcgen05 projections with fused
 SiluAndMul / split-K partial sums) only the summation order differs.
 
 This does not test any kernel (tests/test_gpu_*.py do); it exists so that a typo in the glue of a path that has not
@@ -97,7 +97,7 @@ class CpuOps:
         self._count("store_kv")
         store_kvcache_ref(k, v, self.kv[layer][0], self.kv[layer][1], slot_mapping)
 
-    # ---- staged tcgen05 projections ---------------------------------------------------------------------------------
+    # ---- tcgen05 projections ----------------------------------------------------------------------------------------
     class pdl_off:
         depth = 0
 
@@ -234,7 +234,7 @@ def test_mega_tail_path_glue_is_the_oracle(preset, monkeypatch):
 
 
 @pytest.mark.parametrize("preset", ["tiny", "tiny-g4"])
-def test_staged_tc_linear_path_glue(preset, monkeypatch):
+def test_tc_linear_path_glue(preset, monkeypatch):
     got, want, fake, model = run_product_model(monkeypatch, preset, {"B200_LINEAR": "tc", "B200_LINEAR_CFG": "32,32,64,4,64,4,0"})
     assert model.tc_linear
     layers = model.cfg.num_hidden_layers
@@ -281,7 +281,7 @@ def test_gate_up_only_tc_mode_glue(monkeypatch):
 
 
 def test_fused_lm_head_runner_glue(monkeypatch):
-    """ModelRunner._forward_and_sample with B200_LM_HEAD=fused hands the right tensors to ops.lm_head_sample (staged path)."""
+    """ModelRunner._forward_and_sample with B200_LM_HEAD=fused hands the right tensors to ops.lm_head_sample (opt-in path)."""
     import nanovllm.engine.model_runner as mr
     from nanovllm.models.qwen3 import Qwen3ForCausalLM
     from nanovllm.utils.context import reset_context, set_context
