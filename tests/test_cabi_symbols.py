@@ -47,6 +47,9 @@ def test_host_only_entry_points():
     assert b"not bound" in lib.b200_strerror(-4)
     assert lib.b200_sm_count(None) == 0
     assert lib.b200_decode_workspace_bytes(None, 4, 4) == 0
+    # the per-thread PDL switch returns the previous setting (enabled by default) and is idempotent
+    assert lib.b200_set_pdl(0) == 1 and lib.b200_set_pdl(0) == 0
+    assert lib.b200_set_pdl(1) == 0 and lib.b200_set_pdl(1) == 1
 
 
 def test_no_cpu_fallback(monkeypatch):
