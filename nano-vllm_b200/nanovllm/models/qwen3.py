@@ -93,7 +93,8 @@ class Qwen3ForCausalLM:
         self.tc_cfg = [int(v) for v in os.environ.get("B200_LINEAR_CFG", "64,64,64,8,64,8,1").split(",")]
         self.tc_max_rows = int(os.environ.get("B200_LINEAR_MAX_ROWS", "128" if mode == "auto" else "256"))
         # above 128 rows a CTA row block is added, so fewer k splits cover the SMs (micro-benchmark at 256 rows, split 4 vs 8:
-        # o_proj 7.6 vs 11.2 us, down_proj 8.8 vs 12.5 us incl. the add-norm); B200_LINEAR_SPLITS_BIG overrides
+        # o_proj 7.6 vs 11.2 us, down_proj 8.8 vs 12.5 us incl. the add-norm); B200_LINEAR_SPLITS_BIG overrides.  In the captured step
+        # B200_LINEAR_MAX_ROWS=256 with split 4 measured level with the library path (3 790 vs 3 774 us at 256 rows), so 128 stays.
         self.tc_big_splits = int(os.environ.get("B200_LINEAR_SPLITS_BIG", "4"))
         fit = lambda k, s: next(d for d in range(max(1, min(s, k // 64)), 0, -1) if (k // 64) % d == 0)     # split-K factors must divide the k tiles
         tcc = self.tc_cfg
@@ -104,7 +105,8 @@ class Qwen3ForCausalLM:
             self.tc_big = (fit(self.q_size, min(tcc[3], self.tc_big_splits)), fit(self.inter, min(tcc[5], self.tc_big_splits)))
         # B200_TAIL=mega: in decode steps of up to 256 rows on one GPU, everything between two attention kernels
         # (o_proj, add+norm, gate_up+SiluAndMul, down_proj, add+norm, the next layer's qkv_proj) is ONE persistent launch
-        # (csrc/layer_tail.cu) instead of seven
+        # (csrc/layer_tail.cu) instead of seven.  Measured 58-70 us per layer against 30 us for the chain (r02_layer_tail_microbench.json):
+        # kept as an opt-in experiment, off by default.
         self.mega_tail = os.environ.get("B200_TAIL", "") == "mega" and tp_size == 1
         self.mega_rows = 256
         want = [int(v) for v in os.environ.get("B200_TAIL_SPLITS", "8,8").split(",")]
@@ -118,6 +120,8 @@ class Qwen3ForCausalLM:
         # free.  Attention kernels never overlap each other (an event chain orders them), so HBM always has one streaming
         # kernel and the chain of the other half hides under it.  One GPU, head groups <= 2 (the FMA decode kernel).
         #   B200_DUAL_CFG = "qkv_bn,gate_up_bn,o_bn,o_splits,down_bn,down_splits,ring_slots"
+        # Measured (profiles/r02_two_stream.json): the co-residency works (both = 71.7 us vs 56.9 + 35.5 serial per half layer) but
+        # a half batch costs more than half, so the step is 8 % slower at 256 rows: off by default.
         dual = os.environ.get("B200_DUAL", "0")
         self.dual = dual not in ("0", "", "off") and tp_size == 1 and self.num_heads // self.num_kv_heads <= 2
         self.dual_min = int(os.environ.get("B200_DUAL_MIN", "144"))
