@@ -4,7 +4,8 @@ engine/peer_reduce.py), run with one Python thread per rank and adversarial dela
 What the CUDA kernel relies on, restated here step for step:
   * every rank owns TWO data buffers that alternate between consecutive exchanges, and one flag word per peer;
   * exchange number e on rank r:  (1) the GEMM writes r's partial into buffer e % 2      [previous kernel in the stream]
-                                  (2) r stores e + 1 into flags_of(p)[r] for every peer p  [st.release.sys]
+                                  (2) r stores e + 1 into flags_of(p)[r] for every peer p  [st.release.sys, one thread per
+                                      peer, all at once: the order of these stores is immaterial to the protocol]
                                   (3) r waits until flags_of(r)[p] >= e + 1 for every p    [ld.acquire.sys]
                                   (4) r reads buffer e % 2 of every rank and reduces
   * nothing else orders the ranks: a fast rank may run ahead as far as the flags let it.
